@@ -1,0 +1,597 @@
+// se3mpc.cu -- kernels and C ABI of libse3mpc.so (sm_100a).  See include/se3mpc.h for the boundary and
+// se3mpc_core.cuh for the warp-cooperative interior-point solver.
+//
+// Kernels
+//   se3mpc_solve_kernel   persistent warps (16 per SM), one problem per warp at a time, problems handed out by an
+//                         atomic ticket so that the very different iteration counts of the NLPs do not leave a tail.
+//                         modes: solve (OCSys.ocSolver), objective (solve + reward fused in the epilogue),
+//                         sol_gradient (9 perturbed objectives per sample, quad_policy.py:94-112).
+//   se3mpc_reward_kernel  stand-alone rotor-tip roll-out + gate reward, one warp per trajectory, lanes <-> stages
+//                         (coalesced 13-double state loads): HBM-bound.
+//   se3mpc_solgrad_epilogue  the clip/scale rule of sol_gradient over the 9 rewards of each sample.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "se3mpc.h"
+#include "se3mpc_core.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CTAS_PER_SM = 4;          // 16 resident warps (= problems) per SM; ~40 KB shared memory per CTA
+
+enum : int { MODE_SOLVE = 0, MODE_OBJECTIVE = 1, MODE_SOLGRAD = 2 };
+
+struct KArgs {
+    se3mpc_params par;
+    int nprob;                 // problems handed out (9*B in sol_gradient mode)
+    int mode, round_t, att_dim;
+    const double *x0, *goal, *gate, *tra_pos, *tra_ang, *t, *ulast;
+    double *X, *U, *LAM, *cost, *reward;
+    int32_t *status, *iters, *nfact, *nls;
+    double *kkt_error;
+    double *slots;
+    unsigned int *ticket;
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    se3::Ctx c;
+    c.sm = reinterpret_cast<se3::WarpSmem *>(smem_raw) + warp;
+    c.ws = a.slots + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * se3::SLOT_DOUBLES;
+    const int N = a.par.N;
+
+    for (;;) {
+        unsigned int pb = 0;
+        if (lane == 0) pb = atomicAdd(a.ticket, 1u);
+        pb = __shfl_sync(0xffffffffu, pb, 0);
+        if (pb >= (unsigned)a.nprob) break;
+
+        // ---- instance (uniform registers) ----
+        int src = (int)pb, variant = 0;
+        if (a.mode == MODE_SOLGRAD) { src = (int)pb / 9; variant = (int)pb % 9; }
+        se3::Instance in;
+        for (int i = 0; i < 13; i++) in.x0[i] = a.x0[(size_t)src * 13 + i];
+        double ang[4];
+        for (int i = 0; i < 3; i++) {
+            in.goal[i] = a.goal[(size_t)src * 3 + i];
+            in.tra_pos[i] = a.tra_pos[(size_t)src * 3 + i];
+        }
+        for (int i = 0; i < a.att_dim; i++) ang[i] = a.tra_ang[(size_t)src * a.att_dim + i];
+        double t = a.t[src];
+        bool with_ulast = (a.ulast != nullptr);
+        int round_t = a.round_t;
+        if (a.mode == MODE_SOLGRAD) {
+            // quad_policy.py:97-110: nominal and t-/+0.1 without Ulast, the six one-sided perturbations with it
+            const double delta = 1e-3;
+            if (variant >= 1 && variant <= 3) in.tra_pos[variant - 1] += delta;
+            else if (variant >= 4 && variant <= 6) ang[variant - 4] += delta;
+            else if (variant == 7) t = t - 0.1;
+            else if (variant == 8) t = t + 0.1;
+            if (variant == 0 || variant >= 7) with_ulast = false;
+            round_t = 1;
+        }
+        if (a.att_dim == 4) { for (int i = 0; i < 4; i++) in.tra_q[i] = ang[i]; }
+        else se3::rd2quat(ang, in.tra_q);
+        in.t_tra = round_t ? se3::round1(t) : t;
+        for (int j = 0; j < 4; j++) in.ulast[j] = with_ulast ? a.ulast[(size_t)src * 4 + j] : 0.0;
+
+        const se3::SolveStats st = se3::ipm_solve(c, a.par, in);
+
+        se3::write_outputs(c, a.X ? a.X + (size_t)pb * (N + 1) * 13 : nullptr, a.U ? a.U + (size_t)pb * N * 4 : nullptr,
+                           a.LAM ? a.LAM + (size_t)pb * N * 13 : nullptr);
+        double rew = 0.0;
+        if (a.mode != MODE_SOLVE) {
+            double gate[12], goal[3];
+            for (int i = 0; i < 12; i++) gate[i] = a.gate[(size_t)src * 12 + i];
+            for (int i = 0; i < 3; i++) goal[i] = in.goal[i];
+            rew = se3::reward_warp(a.par, gate, goal,
+                                   [&](int s, double *x) {
+#pragma unroll
+                                       for (int i = 0; i < 13; i++) x[i] = se3::row(c, se3::R_X + i)[s];
+                                   },
+                                   nullptr, nullptr, nullptr);
+        }
+        if (lane == 0) {
+            if (a.cost) a.cost[pb] = st.cost;
+            if (a.reward) a.reward[pb] = rew;
+            if (a.status) a.status[pb] = st.status;
+            if (a.iters) a.iters[pb] = st.iters;
+            if (a.nfact) a.nfact[pb] = st.nfact;
+            if (a.nls) a.nls[pb] = st.nls;
+            if (a.kkt_error) a.kkt_error[pb] = st.kkt_error;
+        }
+        __syncwarp();
+    }
+}
+
+struct RArgs {
+    se3mpc_params par;
+    int B;
+    const double *X, *gate, *goal;
+    double *reward, *collision, *path;
+    int32_t *co;
+};
+
+__global__ void __launch_bounds__(256) se3mpc_reward_kernel(const __grid_constant__ RArgs a)
+{
+    const int warps_per_cta = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int N = a.par.N;
+    for (int pb = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); pb < a.B; pb += gridDim.x * warps_per_cta) {
+        const double *X = a.X + (size_t)pb * (N + 1) * 13;
+        double gate[12], goal[3];
+        for (int i = 0; i < 12; i++) gate[i] = __ldg(a.gate + (size_t)pb * 12 + i);
+        for (int i = 0; i < 3; i++) goal[i] = __ldg(a.goal + (size_t)pb * 3 + i);
+        double col, path;
+        int co;
+        const double r = se3::reward_warp(a.par, gate, goal,
+                                          [&](int s, double *x) {
+#pragma unroll
+                                              for (int i = 0; i < 13; i++) x[i] = __ldg(X + s * 13 + i);
+                                          },
+                                          &col, &path, &co);
+        if (lane == 0) {
+            a.reward[pb] = r;
+            if (a.collision) a.collision[pb] = col;
+            if (a.path) a.path[pb] = path;
+            if (a.co) a.co[pb] = co;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) se3mpc_collis_kernel(int B, int horizon, const double *V, const double *gate, double *score,
+                                                            int32_t *co_out)
+{
+    const int warps_per_cta = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int pb = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); pb < B; pb += gridDim.x * warps_per_cta) {
+        const double *Vp = V + (size_t)pb * (horizon + 1) * 3;
+        double g[12];
+        for (int i = 0; i < 12; i++) g[i] = __ldg(gate + (size_t)pb * 12 + i);
+        int co;
+        const double sc = se3::collis_warp(g, horizon,
+                                           [&](int s, double *v) { v[0] = __ldg(Vp + s * 3); v[1] = __ldg(Vp + s * 3 + 1); v[2] = __ldg(Vp + s * 3 + 2); },
+                                           &co);
+        if (lane == 0) {
+            score[pb] = sc;
+            if (co_out) co_out[pb] = co;
+        }
+    }
+}
+
+// quad_policy.py:98-112 over the 9 rewards of every sample
+__global__ void se3mpc_solgrad_epilogue(int B, const double *rew9, const double *tra_ang, const int32_t *st_in, double *out,
+                                        int32_t *status9)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double *r = rew9 + (size_t)b * 9;
+    const double j = r[0];
+    double o[8];
+    for (int i = 0; i < 3; i++) o[i] = -(fmin(fmax(r[1 + i] - j, -0.5), 0.5) * 0.1);
+    for (int i = 0; i < 3; i++) {
+        const double ai = tra_ang[(size_t)b * 3 + i];
+        o[3 + i] = -(fmin(fmax(r[4 + i] - j, -0.5), 0.5) * (1.0 / (500.0 * ai * ai + 5.0)));
+    }
+    double drdt = 0.0;
+    if (r[7] - j > 2.0) drdt = -0.05;
+    if (r[8] - j > 2.0) drdt = 0.05;
+    o[6] = -drdt;
+    o[7] = j;
+    for (int i = 0; i < 8; i++) out[(size_t)b * 8 + i] = o[i];
+    if (status9)
+        for (int i = 0; i < 9; i++) status9[(size_t)b * 9 + i] = st_in[(size_t)b * 9 + i];
+}
+
+// ------------------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+#define CK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return fail(SE3MPC_ERR_CUDA, #call, e_);   \
+    } while (0)
+
+int have_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int num_sms()
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+constexpr size_t HDR_BYTES = 256;
+
+int slots_for(int nproblems)
+{
+    const int cap = num_sms() * CTAS_PER_SM * WARPS_PER_CTA;
+    int s = nproblems < cap ? nproblems : cap;
+    s = (s + WARPS_PER_CTA - 1) / WARPS_PER_CTA * WARPS_PER_CTA;
+    return s < WARPS_PER_CTA ? WARPS_PER_CTA : s;
+}
+
+bool params_ok(const se3mpc_params *p)
+{
+    return p && p->N >= 2 && p->N <= SE3MPC_MAX_HORIZON && (p->att_power == 1 || p->att_power == 2) && p->dt > 0 &&
+           p->u_ub > p->u_lb && p->w_bound > 0 && p->mass > 0;
+}
+
+// workspace: [ticket | pad to 256 B][aux doubles: nprob][aux int32: nprob][slots]
+struct WsLayout { unsigned int *ticket; double *aux_d; int32_t *aux_i; double *slots; int nslots; size_t bytes; };
+
+WsLayout layout(void *ws, int nproblems)
+{
+    WsLayout L;
+    unsigned char *b = static_cast<unsigned char *>(ws);
+    size_t off = HDR_BYTES;
+    L.ticket = reinterpret_cast<unsigned int *>(b);
+    L.aux_d = reinterpret_cast<double *>(b + off);
+    off += ((size_t)nproblems * sizeof(double) + 255) / 256 * 256;
+    L.aux_i = reinterpret_cast<int32_t *>(b + off);
+    off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
+    L.slots = reinterpret_cast<double *>(b + off);
+    L.nslots = slots_for(nproblems);
+    off += (size_t)L.nslots * se3::SLOT_DOUBLES * sizeof(double);
+    L.bytes = off;
+    return L;
+}
+
+int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, const double *x0, const double *goal,
+                  const double *gate, const double *tra_pos, const double *tra_ang, int att_dim, const double *t, const double *ulast,
+                  double *X, double *U, double *LAM, double *cost, double *reward, const se3mpc_stats *stats,
+                  int32_t *status_override, void *workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    if (nprob <= 0) return SE3MPC_OK;
+    WsLayout L = layout(workspace, nprob);
+    if (!workspace || workspace_bytes < L.bytes) return fail(SE3MPC_ERR_WORKSPACE, "workspace too small");
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.par = *p; a.nprob = nprob; a.mode = mode; a.round_t = round_t; a.att_dim = att_dim;
+    a.x0 = x0; a.goal = goal; a.gate = gate; a.tra_pos = tra_pos; a.tra_ang = tra_ang; a.t = t; a.ulast = ulast;
+    a.X = X; a.U = U; a.LAM = LAM; a.cost = cost; a.reward = reward;
+    if (stats) { a.status = stats->status; a.iters = stats->iters; a.nfact = stats->nfact; a.nls = stats->nls; a.kkt_error = stats->kkt_error; }
+    if (status_override) a.status = status_override;
+    a.slots = L.slots; a.ticket = L.ticket;
+    CK(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), stream));
+    const size_t smem = sizeof(se3::WarpSmem) * WARPS_PER_CTA;
+    static std::once_flag once;
+    std::call_once(once, [&] { cudaFuncSetAttribute(se3mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    const int grid = L.nslots / WARPS_PER_CTA;
+    se3mpc_solve_kernel<<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void se3mpc_default_params(se3mpc_params *p)
+{
+    memset(p, 0, sizeof(*p));
+    p->Jx = 0.0023; p->Jy = 0.0023; p->Jz = 0.004; p->mass = 0.5; p->arm_l = 0.35; p->c_tau = 0.0245;   // quad_policy.py:37
+    p->grav = 9.78;                                                                                   // quad_model.py:37
+    p->wrt = 5; p->wqt = 80; p->wthrust = 0.1; p->wrf = 5; p->wvf = 5; p->wwf = 3;                    // quad_policy.py:38
+    p->wdu = 1.0;                                                                                     // quad_OC.py:150
+    p->gamma_amp = 60.0; p->gamma_rate = 10.0;                                                        // quad_OC.py:145
+    p->dt = 0.1;                                                                                      // quad_policy.py:43
+    p->u_lb = 0.0; p->u_ub = 2.0 * 1.22;                                                              // quad_policy.py:48-51
+    p->w_bound = 3.14159265358979323846 / 2.0;                                                        // quad_policy.py:47
+    p->wing_len = 1.5;                                                                                // quad_policy.py:19
+    p->N = 50;                                                                                        // quad_policy.py:17
+    p->att_power = 2;                                                                                 // quad_model.py:210
+    p->tol = 1e-8; p->acceptable_tol = 1e-6; p->mu_init = 0.1;                                        // IPOPT defaults
+    p->max_iter = 3000; p->acceptable_iter = 15; p->max_soc = 4;
+    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT;
+}
+
+const char *se3mpc_last_error(void) { return g_err; }
+int se3mpc_device_count(void) { return have_device(); }
+const char *se3mpc_version(void) { return "se3mpc 0.1 (sm_100a)"; }
+long long se3mpc_launch_count(void) { return g_launches.load(); }
+
+size_t se3mpc_workspace_bytes(const se3mpc_params *p, int nproblems)
+{
+    if (!params_ok(p) || nproblems <= 0 || !have_device()) return 0;
+    return layout(nullptr, nproblems).bytes;
+}
+
+int se3mpc_solve_device(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *tra_pos,
+                        const double *tra_ang, int att_dim, const double *t, const double *ulast, int round_t, double *X, double *U,
+                        double *LAM, double *cost, const se3mpc_stats *stats, void *workspace, size_t workspace_bytes,
+                        void *stream)
+{
+    if (!params_ok(p) || B < 0 || !x0 || !goal || !tra_pos || !tra_ang || !t || (att_dim != 3 && att_dim != 4))
+        return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    return launch_solver(p, MODE_SOLVE, B, round_t, x0, goal, nullptr, tra_pos, tra_ang, att_dim, t, ulast, X, U, LAM, cost, nullptr,
+                         stats, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const double *gate, const double *goal,
+                         double *reward, double *collision, double *path, int32_t *co, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !X || !gate || !goal || !reward) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    RArgs a;
+    a.par = *p; a.B = B; a.X = X; a.gate = gate; a.goal = goal; a.reward = reward; a.collision = collision; a.path = path; a.co = co;
+    const int warps_per_cta = 8;
+    int grid = (B + warps_per_cta - 1) / warps_per_cta;
+    const int cap = num_sms() * 8;
+    if (grid > cap) grid = cap;
+    se3mpc_reward_kernel<<<grid, warps_per_cta * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_collis_det_device(int B, int horizon, const double *V, const double *gate, double *score, int32_t *co, void *stream)
+{
+    if (B < 0 || horizon < 1 || !V || !gate || !score) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    const int warps_per_cta = 8;
+    int grid = (B + warps_per_cta - 1) / warps_per_cta;
+    const int cap = num_sms() * 8;
+    if (grid > cap) grid = cap;
+    se3mpc_collis_kernel<<<grid, warps_per_cta * 32, 0, static_cast<cudaStream_t>(stream)>>>(B, horizon, V, gate, score, co);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_objective_device(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *gate,
+                            const double *tra_pos, const double *tra_ang, const double *t, const double *ulast,
+                            double *reward, double *X, double *U, double *cost, const se3mpc_stats *stats, void *workspace,
+                            size_t workspace_bytes, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !x0 || !goal || !gate || !tra_pos || !tra_ang || !t || !reward)
+        return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    return launch_solver(p, MODE_OBJECTIVE, B, 1, x0, goal, gate, tra_pos, tra_ang, 3, t, ulast, X, U, nullptr, cost, reward, stats,
+                         nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int se3mpc_sol_gradient_device(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *gate,
+                               const double *tra_pos, const double *tra_ang, const double *t, const double *ulast,
+                               double *out, int32_t *status9, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !x0 || !goal || !gate || !tra_pos || !tra_ang || !t || !out)
+        return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    const int nprob = 9 * B;
+    WsLayout L = layout(workspace, nprob);
+    if (!workspace || workspace_bytes < L.bytes) return fail(SE3MPC_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = launch_solver(p, MODE_SOLGRAD, nprob, 1, x0, goal, gate, tra_pos, tra_ang, 3, t, ulast, nullptr, nullptr, nullptr, nullptr,
+                           L.aux_d, nullptr, L.aux_i, workspace, workspace_bytes, s);
+    if (rc != SE3MPC_OK) return rc;
+    se3mpc_solgrad_epilogue<<<(B + 127) / 128, 128, 0, s>>>(B, L.aux_d, tra_ang, L.aux_i, out, status9);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-buffer entry points: stage through cached device buffers
+// ------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return SE3MPC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return fail(SE3MPC_ERR_CUDA, "cudaMalloc", e);
+        cap = n;
+        return SE3MPC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+std::mutex g_host_mu;
+DevBuf g_in, g_out, g_ws;
+cudaStream_t g_stream = nullptr;
+
+struct Arena {
+    unsigned char *base;
+    size_t off = 0;
+    template <class T> T *take(size_t n) { T *r = reinterpret_cast<T *>(base + off); off += (n * sizeof(T) + 255) / 256 * 256; return r; }
+};
+size_t pad(size_t n) { return (n + 255) / 256 * 256; }
+
+int host_common(const se3mpc_params *p, int mode, int B, const double *x0, const double *goal, const double *gate,
+                const double *tra_pos, const double *tra_ang, int att_dim, const double *t, const double *ulast, int round_t, double *X,
+                double *U, double *LAM, double *cost, double *reward, double *out8, int32_t *status9, const se3mpc_stats *stats)
+{
+    if (!params_ok(p) || B < 0 || !x0 || !goal || !tra_pos || !tra_ang || !t || (att_dim != 3 && att_dim != 4))
+        return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (mode != MODE_SOLVE && !gate) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    const int N = p->N;
+    const int nprob = (mode == MODE_SOLGRAD) ? 9 * B : B;
+    const size_t in_bytes = pad((size_t)B * 13 * 8) + 2 * pad((size_t)B * 3 * 8) + pad((size_t)B * 4 * 8) + pad((size_t)B * 12 * 8) + pad((size_t)B * 8) + pad((size_t)B * 4 * 8);
+    const size_t out_bytes = pad((size_t)nprob * (N + 1) * 13 * 8) + pad((size_t)nprob * N * 4 * 8) + pad((size_t)nprob * N * 13 * 8) +
+                             3 * pad((size_t)nprob * 8) + 4 * pad((size_t)nprob * 4) + pad((size_t)B * 8 * 8) + pad((size_t)B * 9 * 4);
+    int rc;
+    if ((rc = g_in.ensure(in_bytes)) != SE3MPC_OK) return rc;
+    if ((rc = g_out.ensure(out_bytes)) != SE3MPC_OK) return rc;
+    const size_t ws_bytes = layout(nullptr, nprob).bytes;
+    if ((rc = g_ws.ensure(ws_bytes)) != SE3MPC_OK) return rc;
+    Arena ai{static_cast<unsigned char *>(g_in.p)}, ao{static_cast<unsigned char *>(g_out.p)};
+    double *d_x0 = ai.take<double>((size_t)B * 13), *d_goal = ai.take<double>((size_t)B * 3), *d_tp = ai.take<double>((size_t)B * 3);
+    double *d_ta = ai.take<double>((size_t)B * 4), *d_gate = ai.take<double>((size_t)B * 12), *d_t = ai.take<double>((size_t)B);
+    double *d_ul = ai.take<double>((size_t)B * 4);
+    double *d_X = ao.take<double>((size_t)nprob * (N + 1) * 13), *d_U = ao.take<double>((size_t)nprob * N * 4);
+    double *d_LAM = ao.take<double>((size_t)nprob * N * 13), *d_cost = ao.take<double>((size_t)nprob), *d_rew = ao.take<double>((size_t)nprob);
+    double *d_kkt = ao.take<double>((size_t)nprob);
+    int32_t *d_st = ao.take<int32_t>((size_t)nprob), *d_it = ao.take<int32_t>((size_t)nprob), *d_nf = ao.take<int32_t>((size_t)nprob);
+    int32_t *d_nl = ao.take<int32_t>((size_t)nprob);
+    double *d_out8 = ao.take<double>((size_t)B * 8);
+    int32_t *d_st9 = ao.take<int32_t>((size_t)B * 9);
+    cudaStream_t s = g_stream;
+    CK(cudaMemcpyAsync(d_x0, x0, (size_t)B * 13 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_goal, goal, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_tp, tra_pos, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ta, tra_ang, (size_t)B * att_dim * 8, cudaMemcpyHostToDevice, s));
+    if (gate) CK(cudaMemcpyAsync(d_gate, gate, (size_t)B * 12 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_t, t, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+    if (ulast) CK(cudaMemcpyAsync(d_ul, ulast, (size_t)B * 4 * 8, cudaMemcpyHostToDevice, s));
+    se3mpc_stats dst = {d_st, d_it, d_nf, d_nl, d_kkt};
+    if (mode == MODE_SOLVE)
+        rc = se3mpc_solve_device(p, B, d_x0, d_goal, d_tp, d_ta, att_dim, d_t, ulast ? d_ul : nullptr, round_t, X ? d_X : nullptr,
+                                 U ? d_U : nullptr, LAM ? d_LAM : nullptr, d_cost, &dst, g_ws.p, g_ws.cap, s);
+    else if (mode == MODE_OBJECTIVE)
+        rc = se3mpc_objective_device(p, B, d_x0, d_goal, d_gate, d_tp, d_ta, d_t, ulast ? d_ul : nullptr, d_rew, X ? d_X : nullptr,
+                                     U ? d_U : nullptr, d_cost, &dst, g_ws.p, g_ws.cap, s);
+    else
+        rc = se3mpc_sol_gradient_device(p, B, d_x0, d_goal, d_gate, d_tp, d_ta, d_t, ulast ? d_ul : nullptr, d_out8, d_st9, g_ws.p,
+                                        g_ws.cap, s);
+    if (rc != SE3MPC_OK) return rc;
+    if (mode == MODE_SOLGRAD) {
+        CK(cudaMemcpyAsync(out8, d_out8, (size_t)B * 8 * 8, cudaMemcpyDeviceToHost, s));
+        if (status9) CK(cudaMemcpyAsync(status9, d_st9, (size_t)B * 9 * 4, cudaMemcpyDeviceToHost, s));
+    } else {
+        if (X) CK(cudaMemcpyAsync(X, d_X, (size_t)B * (N + 1) * 13 * 8, cudaMemcpyDeviceToHost, s));
+        if (U) CK(cudaMemcpyAsync(U, d_U, (size_t)B * N * 4 * 8, cudaMemcpyDeviceToHost, s));
+        if (LAM) CK(cudaMemcpyAsync(LAM, d_LAM, (size_t)B * N * 13 * 8, cudaMemcpyDeviceToHost, s));
+        if (cost) CK(cudaMemcpyAsync(cost, d_cost, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+        if (reward) CK(cudaMemcpyAsync(reward, d_rew, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+        if (stats) {
+            if (stats->status) CK(cudaMemcpyAsync(stats->status, d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            if (stats->iters) CK(cudaMemcpyAsync(stats->iters, d_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            if (stats->nfact) CK(cudaMemcpyAsync(stats->nfact, d_nf, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            if (stats->nls) CK(cudaMemcpyAsync(stats->nls, d_nl, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            if (stats->kkt_error) CK(cudaMemcpyAsync(stats->kkt_error, d_kkt, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CK(cudaStreamSynchronize(s));
+    return SE3MPC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int se3mpc_solve_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *tra_pos,
+                      const double *tra_ang, int att_dim, const double *t, const double *ulast, int round_t, double *X, double *U,
+                      double *LAM, double *cost, const se3mpc_stats *stats)
+{
+    return host_common(p, MODE_SOLVE, B, x0, goal, nullptr, tra_pos, tra_ang, att_dim, t, ulast, round_t, X, U, LAM, cost, nullptr, nullptr,
+                       nullptr, stats);
+}
+
+int se3mpc_objective_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *gate,
+                          const double *tra_pos, const double *tra_ang, const double *t, const double *ulast, double *reward,
+                          double *X, double *U, double *cost, const se3mpc_stats *stats)
+{
+    if (!reward) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    return host_common(p, MODE_OBJECTIVE, B, x0, goal, gate, tra_pos, tra_ang, 3, t, ulast, 1, X, U, nullptr, cost, reward, nullptr,
+                       nullptr, stats);
+}
+
+int se3mpc_sol_gradient_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *gate,
+                             const double *tra_pos, const double *tra_ang, const double *t, const double *ulast, double *out,
+                             int32_t *status9)
+{
+    if (!out) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    return host_common(p, MODE_SOLGRAD, B, x0, goal, gate, tra_pos, tra_ang, 3, t, ulast, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       out, status9, nullptr);
+}
+
+int se3mpc_reward_host(const se3mpc_params *p, int B, const double *X, const double *gate, const double *goal, double *reward,
+                       double *collision, double *path, int32_t *co)
+{
+    if (!params_ok(p) || B < 0 || !X || !gate || !goal || !reward) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    const int N = p->N;
+    int rc;
+    const size_t xb = (size_t)B * (N + 1) * 13 * 8;
+    if ((rc = g_in.ensure(pad(xb) + pad((size_t)B * 12 * 8) + pad((size_t)B * 3 * 8))) != SE3MPC_OK) return rc;
+    if ((rc = g_out.ensure(3 * pad((size_t)B * 8) + pad((size_t)B * 4))) != SE3MPC_OK) return rc;
+    Arena ai{static_cast<unsigned char *>(g_in.p)}, ao{static_cast<unsigned char *>(g_out.p)};
+    double *d_X = ai.take<double>((size_t)B * (N + 1) * 13), *d_gate = ai.take<double>((size_t)B * 12), *d_goal = ai.take<double>((size_t)B * 3);
+    double *d_r = ao.take<double>(B), *d_c = ao.take<double>(B), *d_p = ao.take<double>(B);
+    int32_t *d_co = ao.take<int32_t>(B);
+    cudaStream_t s = g_stream;
+    CK(cudaMemcpyAsync(d_X, X, xb, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_gate, gate, (size_t)B * 12 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_goal, goal, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, s));
+    rc = se3mpc_reward_device(p, B, d_X, d_gate, d_goal, d_r, d_c, d_p, d_co, s);
+    if (rc != SE3MPC_OK) return rc;
+    CK(cudaMemcpyAsync(reward, d_r, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (collision) CK(cudaMemcpyAsync(collision, d_c, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (path) CK(cudaMemcpyAsync(path, d_p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (co) CK(cudaMemcpyAsync(co, d_co, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SE3MPC_OK;
+}
+
+int se3mpc_collis_det_host(int B, int horizon, const double *V, const double *gate, double *score, int32_t *co)
+{
+    if (B < 0 || horizon < 1 || !V || !gate || !score) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    int rc;
+    const size_t vb = (size_t)B * (horizon + 1) * 3 * 8;
+    if ((rc = g_in.ensure(pad(vb) + pad((size_t)B * 12 * 8))) != SE3MPC_OK) return rc;
+    if ((rc = g_out.ensure(pad((size_t)B * 8) + pad((size_t)B * 4))) != SE3MPC_OK) return rc;
+    Arena ai{static_cast<unsigned char *>(g_in.p)}, ao{static_cast<unsigned char *>(g_out.p)};
+    double *d_V = ai.take<double>((size_t)B * (horizon + 1) * 3), *d_gate = ai.take<double>((size_t)B * 12);
+    double *d_s = ao.take<double>(B);
+    int32_t *d_co = ao.take<int32_t>(B);
+    cudaStream_t s = g_stream;
+    CK(cudaMemcpyAsync(d_V, V, vb, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_gate, gate, (size_t)B * 12 * 8, cudaMemcpyHostToDevice, s));
+    rc = se3mpc_collis_det_device(B, horizon, d_V, d_gate, d_s, d_co, s);
+    if (rc != SE3MPC_OK) return rc;
+    CK(cudaMemcpyAsync(score, d_s, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (co) CK(cudaMemcpyAsync(co, d_co, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SE3MPC_OK;
+}
+
+void se3mpc_host_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    g_in.release(); g_out.release(); g_ws.release();
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+}
+
+}  // extern "C"

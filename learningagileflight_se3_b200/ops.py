@@ -1,0 +1,281 @@
+"""Batched operators over the C ABI (include/se3mpc.h).
+
+Two faces, same kernels:
+  * device tensors (torch.float64 on CUDA): `solve`, `reward`, `objective`, `sol_gradient` enqueue on the current
+    torch stream and return device tensors; also registered as `torch.ops.se3mpc.*` (CUDA only, no CPU kernel).
+  * host buffers (numpy): `solve_host`, `reward_host`, `objective_host`, `sol_gradient_host` -- the call a user of
+    the reference makes (numpy in, numpy out), with H2D / D2H inside the library.
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Params, Se3MpcError, Stats, default_params  # noqa: F401
+
+_workspaces: dict = {}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise Se3MpcError("se3mpc device ops need CUDA tensors (there is no CPU fallback)")
+        if t.dtype != torch.float64:
+            raise Se3MpcError("se3mpc device ops compute in float64; got %s" % t.dtype)
+
+
+def _c(t: Optional[torch.Tensor], shape):
+    if t is None:
+        return None
+    return t.reshape(shape).contiguous()
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _workspace(p: Params, nproblems: int, device) -> torch.Tensor:
+    need = int(_lib.lib().se3mpc_workspace_bytes(C.byref(p), int(nproblems)))
+    if need == 0:
+        raise Se3MpcError("se3mpc_workspace_bytes returned 0 (bad params or no CUDA device)")
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _stats(B, device):
+    st = {k: torch.empty(B, dtype=torch.int32, device=device) for k in ("status", "iters", "nfact", "nls")}
+    st["kkt_error"] = torch.empty(B, dtype=torch.float64, device=device)
+    cs = Stats(st["status"].data_ptr(), st["iters"].data_ptr(), st["nfact"].data_ptr(), st["nls"].data_ptr(), st["kkt_error"].data_ptr())
+    return st, cs
+
+
+def solve(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Optional[Params] = None,
+          want_traj=True, want_costate=True):
+    """OCSys.ocSolver for a batch (quad_OC.py:104-212).  Returns dict of device tensors.
+
+    tra_ang is [B,3] (the planner's Rodrigues-like vector, converted on the device) or [B,4] (traversal quaternion)."""
+    p = params or default_params()
+    _require_cuda(x0, goal, tra_pos, tra_ang, t, ulast)
+    B, N, dev = x0.reshape(-1, 13).shape[0], p.N, x0.device
+    att_dim = 4 if tra_ang.numel() == 4 * B else 3
+    x0, goal, tra_pos, tra_ang, t = _c(x0, (B, 13)), _c(goal, (B, 3)), _c(tra_pos, (B, 3)), _c(tra_ang, (B, att_dim)), _c(t, (B,))
+    ulast = _c(ulast, (B, 4))
+    X = torch.empty((B, N + 1, 13), dtype=torch.float64, device=dev) if want_traj else None
+    U = torch.empty((B, N, 4), dtype=torch.float64, device=dev) if want_traj else None
+    LAM = torch.empty((B, N, 13), dtype=torch.float64, device=dev) if want_costate else None
+    cost = torch.empty(B, dtype=torch.float64, device=dev)
+    st, cs = _stats(B, dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(p, B, dev)
+        rc = _lib.lib().se3mpc_solve_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(tra_pos), _ptr(tra_ang), att_dim, _ptr(t), _ptr(ulast),
+                                            int(bool(round_t)), _ptr(X), _ptr(U), _ptr(LAM), _ptr(cost), C.byref(cs), _ptr(ws),
+                                            ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_solve_device")
+    return {"state_traj_opt": X, "control_traj_opt": U, "costate_traj_opt": LAM, "cost": cost, **st}
+
+
+def reward(X, gate, goal, params: Optional[Params] = None):
+    """get_quadrotor_position + 4x collis_det + path + reward (quad_policy.py:78-91) for a batch of trajectories."""
+    p = params or default_params()
+    _require_cuda(X, gate, goal)
+    N = p.N
+    B, dev = X.reshape(-1, N + 1, 13).shape[0], X.device
+    X, gate, goal = _c(X, (B, N + 1, 13)), _c(gate, (B, 12)), _c(goal, (B, 3))
+    r = torch.empty(B, dtype=torch.float64, device=dev)
+    col, path = torch.empty_like(r), torch.empty_like(r)
+    co = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().se3mpc_reward_device(C.byref(p), B, _ptr(X), _ptr(gate), _ptr(goal), _ptr(r), _ptr(col), _ptr(path), _ptr(co),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_reward_device")
+    return {"reward": r, "collision": col, "path": path, "co": co}
+
+
+def objective(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: Optional[Params] = None, want_traj=False):
+    """run_quad.objective for a batch (quad_policy.py:67-91): t rounded to 0.1, solve, reward -- one launch."""
+    p = params or default_params()
+    _require_cuda(x0, goal, gate, tra_pos, tra_ang, t, ulast)
+    B, N, dev = x0.reshape(-1, 13).shape[0], p.N, x0.device
+    x0, goal, gate = _c(x0, (B, 13)), _c(goal, (B, 3)), _c(gate, (B, 12))
+    tra_pos, tra_ang, t, ulast = _c(tra_pos, (B, 3)), _c(tra_ang, (B, 3)), _c(t, (B,)), _c(ulast, (B, 4))
+    r = torch.empty(B, dtype=torch.float64, device=dev)
+    cost = torch.empty_like(r)
+    X = torch.empty((B, N + 1, 13), dtype=torch.float64, device=dev) if want_traj else None
+    U = torch.empty((B, N, 4), dtype=torch.float64, device=dev) if want_traj else None
+    st, cs = _stats(B, dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(p, B, dev)
+        rc = _lib.lib().se3mpc_objective_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(gate), _ptr(tra_pos), _ptr(tra_ang), _ptr(t),
+                                                _ptr(ulast), _ptr(r), _ptr(X), _ptr(U), _ptr(cost), C.byref(cs), _ptr(ws), ws.numel(),
+                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_objective_device")
+    return {"reward": r, "cost": cost, "state_traj_opt": X, "control_traj_opt": U, **st}
+
+
+def sol_gradient(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: Optional[Params] = None):
+    """run_quad.sol_gradient for a batch (quad_policy.py:94-112): 9 solves per sample in one launch -> [B,8]."""
+    p = params or default_params()
+    _require_cuda(x0, goal, gate, tra_pos, tra_ang, t, ulast)
+    B, dev = x0.reshape(-1, 13).shape[0], x0.device
+    x0, goal, gate = _c(x0, (B, 13)), _c(goal, (B, 3)), _c(gate, (B, 12))
+    tra_pos, tra_ang, t, ulast = _c(tra_pos, (B, 3)), _c(tra_ang, (B, 3)), _c(t, (B,)), _c(ulast, (B, 4))
+    out = torch.empty((B, 8), dtype=torch.float64, device=dev)
+    st9 = torch.empty((B, 9), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(p, 9 * B, dev)
+        rc = _lib.lib().se3mpc_sol_gradient_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(gate), _ptr(tra_pos), _ptr(tra_ang), _ptr(t),
+                                                   _ptr(ulast), _ptr(out), _ptr(st9), _ptr(ws), ws.numel(),
+                                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_sol_gradient_device")
+    return out, st9
+
+
+# ---- host-buffer face (numpy in / numpy out; H2D + kernels + D2H inside libse3mpc.so) ----------------------
+def _np(a, shape):
+    return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(shape)
+
+
+def _np_ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _np_stats(B):
+    st = {k: np.empty(B, dtype=np.int32) for k in ("status", "iters", "nfact", "nls")}
+    st["kkt_error"] = np.empty(B, dtype=np.float64)
+    cs = Stats(st["status"].ctypes.data, st["iters"].ctypes.data, st["nfact"].ctypes.data, st["nls"].ctypes.data,
+               st["kkt_error"].ctypes.data)
+    return st, cs
+
+
+def solve_host(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Optional[Params] = None,
+               want_traj=True, want_costate=True):
+    p = params or default_params()
+    x0 = _np(x0, (-1, 13))
+    B, N = x0.shape[0], p.N
+    att_dim = 4 if np.asarray(tra_ang).size == 4 * B else 3
+    goal, tra_pos, tra_ang, t, ulast = _np(goal, (B, 3)), _np(tra_pos, (B, 3)), _np(tra_ang, (B, att_dim)), _np(t, (B,)), _np(ulast, (B, 4))
+    X = np.empty((B, N + 1, 13)) if want_traj else None
+    U = np.empty((B, N, 4)) if want_traj else None
+    LAM = np.empty((B, N, 13)) if want_costate else None
+    cost = np.empty(B)
+    st, cs = _np_stats(B)
+    rc = _lib.lib().se3mpc_solve_host(C.byref(p), B, _np_ptr(x0), _np_ptr(goal), _np_ptr(tra_pos), _np_ptr(tra_ang), att_dim, _np_ptr(t),
+                                      _np_ptr(ulast), int(bool(round_t)), _np_ptr(X), _np_ptr(U), _np_ptr(LAM), _np_ptr(cost), C.byref(cs))
+    _lib.check(rc, "se3mpc_solve_host")
+    return {"state_traj_opt": X, "control_traj_opt": U, "costate_traj_opt": LAM, "cost": cost, **st}
+
+
+def reward_host(X, gate, goal, params: Optional[Params] = None):
+    p = params or default_params()
+    N = p.N
+    X = _np(X, (-1, N + 1, 13))
+    B = X.shape[0]
+    gate, goal = _np(gate, (B, 12)), _np(goal, (B, 3))
+    r, col, path, co = np.empty(B), np.empty(B), np.empty(B), np.empty(B, dtype=np.int32)
+    rc = _lib.lib().se3mpc_reward_host(C.byref(p), B, _np_ptr(X), _np_ptr(gate), _np_ptr(goal), _np_ptr(r), _np_ptr(col), _np_ptr(path),
+                                       C.c_void_p(co.ctypes.data))
+    _lib.check(rc, "se3mpc_reward_host")
+    return {"reward": r, "collision": col, "path": path, "co": co}
+
+
+def collis_det_host(V, gate, horizon):
+    """obstacle.collis_det for B polylines V[B,horizon+1,3] (solid_geometry.py:104-168) -> (score[B], co[B])."""
+    V = _np(V, (-1, horizon + 1, 3))
+    B = V.shape[0]
+    gate = _np(gate, (B, 12))
+    score, co = np.empty(B), np.empty(B, dtype=np.int32)
+    rc = _lib.lib().se3mpc_collis_det_host(B, int(horizon), _np_ptr(V), _np_ptr(gate), _np_ptr(score), C.c_void_p(co.ctypes.data))
+    _lib.check(rc, "se3mpc_collis_det_host")
+    return score, co
+
+
+def collis_det(V, gate, horizon):
+    """Device-tensor variant of collis_det_host."""
+    _require_cuda(V, gate)
+    B, dev = V.reshape(-1, horizon + 1, 3).shape[0], V.device
+    V, gate = _c(V, (B, horizon + 1, 3)), _c(gate, (B, 12))
+    score = torch.empty(B, dtype=torch.float64, device=dev)
+    co = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().se3mpc_collis_det_device(B, int(horizon), _ptr(V), _ptr(gate), _ptr(score), _ptr(co),
+                                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_collis_det_device")
+    return score, co
+
+
+def objective_host(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: Optional[Params] = None, want_traj=False):
+    p = params or default_params()
+    x0 = _np(x0, (-1, 13))
+    B, N = x0.shape[0], p.N
+    goal, gate = _np(goal, (B, 3)), _np(gate, (B, 12))
+    tra_pos, tra_ang, t, ulast = _np(tra_pos, (B, 3)), _np(tra_ang, (B, 3)), _np(t, (B,)), _np(ulast, (B, 4))
+    r, cost = np.empty(B), np.empty(B)
+    X = np.empty((B, N + 1, 13)) if want_traj else None
+    U = np.empty((B, N, 4)) if want_traj else None
+    st, cs = _np_stats(B)
+    rc = _lib.lib().se3mpc_objective_host(C.byref(p), B, _np_ptr(x0), _np_ptr(goal), _np_ptr(gate), _np_ptr(tra_pos), _np_ptr(tra_ang),
+                                          _np_ptr(t), _np_ptr(ulast), _np_ptr(r), _np_ptr(X), _np_ptr(U), _np_ptr(cost), C.byref(cs))
+    _lib.check(rc, "se3mpc_objective_host")
+    return {"reward": r, "cost": cost, "state_traj_opt": X, "control_traj_opt": U, **st}
+
+
+def sol_gradient_host(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: Optional[Params] = None):
+    p = params or default_params()
+    x0 = _np(x0, (-1, 13))
+    B = x0.shape[0]
+    goal, gate = _np(goal, (B, 3)), _np(gate, (B, 12))
+    tra_pos, tra_ang, t, ulast = _np(tra_pos, (B, 3)), _np(tra_ang, (B, 3)), _np(t, (B,)), _np(ulast, (B, 4))
+    out = np.empty((B, 8))
+    st9 = np.empty((B, 9), dtype=np.int32)
+    rc = _lib.lib().se3mpc_sol_gradient_host(C.byref(p), B, _np_ptr(x0), _np_ptr(goal), _np_ptr(gate), _np_ptr(tra_pos), _np_ptr(tra_ang),
+                                             _np_ptr(t), _np_ptr(ulast), _np_ptr(out), C.c_void_p(st9.ctypes.data))
+    _lib.check(rc, "se3mpc_sol_gradient_host")
+    return out, st9
+
+
+# ---- torch custom ops: torch.ops.se3mpc.{solve,reward,objective,sol_gradient} (CUDA dispatch key only) ------
+_registered = False
+
+
+def register_torch_ops():
+    """Thin torch.library registration over the C ABI; default parameters (reference literals). CUDA only."""
+    global _registered
+    if _registered:
+        return
+    lib_def = torch.library.Library("se3mpc", "DEF")
+    lib_def.define("solve(Tensor x0, Tensor goal, Tensor tra_pos, Tensor tra_ang, Tensor t, Tensor? ulast, bool round_t) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+    lib_def.define("reward(Tensor X, Tensor gate, Tensor goal) -> Tensor")
+    lib_def.define("objective(Tensor x0, Tensor goal, Tensor gate, Tensor tra_pos, Tensor tra_ang, Tensor t, Tensor? ulast) -> (Tensor, Tensor)")
+    lib_def.define("sol_gradient(Tensor x0, Tensor goal, Tensor gate, Tensor tra_pos, Tensor tra_ang, Tensor t, Tensor? ulast) -> Tensor")
+
+    def _solve(x0, goal, tra_pos, tra_ang, t, ulast, round_t):
+        r = solve(x0, goal, tra_pos, tra_ang, t, ulast, round_t)
+        return r["state_traj_opt"], r["control_traj_opt"], r["costate_traj_opt"], r["cost"], r["status"]
+
+    def _reward(X, gate, goal):
+        return reward(X, gate, goal)["reward"]
+
+    def _objective(x0, goal, gate, tra_pos, tra_ang, t, ulast):
+        r = objective(x0, goal, gate, tra_pos, tra_ang, t, ulast)
+        return r["reward"], r["status"]
+
+    def _sol_gradient(x0, goal, gate, tra_pos, tra_ang, t, ulast):
+        return sol_gradient(x0, goal, gate, tra_pos, tra_ang, t, ulast)[0]
+
+    lib_def.impl("solve", _solve, "CUDA")
+    lib_def.impl("reward", _reward, "CUDA")
+    lib_def.impl("objective", _objective, "CUDA")
+    lib_def.impl("sol_gradient", _sol_gradient, "CUDA")
+    globals()["_torch_lib"] = lib_def
+    _registered = True

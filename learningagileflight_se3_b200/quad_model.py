@@ -1,0 +1,125 @@
+"""Host-side mirror of the parts of the reference's quad_model.py that feed the hot path.
+
+`Quadrotor` keeps the reference's method names (initDyn / initCost / init_TraCost / setDyn /
+get_quadrotor_position, quad_model.py:14-276) but holds NUMBERS, not casadi expressions: the dynamics, costs and
+their derivatives live as device functions in csrc/se3mpc_core.cuh.  The attributes the reference hands to OCSys
+(`X, U, f, thrust_cost, goal_cost, tra_cost, final_cost`) are opaque tokens that `quad_OC.OCSys` recognises.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def toQuaternion(angle, dir):
+    """Axis-angle to scalar-first quaternion, same contract as quad_model.py:818-825 (returns a list)."""
+    d = np.asarray(dir, dtype=float)
+    d = d / np.linalg.norm(d)
+    h = 0.5 * float(angle)
+    s = math.sin(h)
+    return [math.cos(h), s * d[0], s * d[1], s * d[2]]
+
+
+class _Token:
+    """Opaque stand-in for a casadi expression; remembers which model quantity it denotes."""
+
+    def __init__(self, owner, kind, n=1):
+        self.owner, self.kind, self._n = owner, kind, n
+
+    def numel(self):
+        return self._n
+
+    def __repr__(self):
+        return f"<se3mpc {self.kind}>"
+
+
+class Quadrotor:
+    def __init__(self, project_name="my UAV"):
+        self.project_name = project_name
+        self.X = _Token(self, "state", 13)
+        self.U = _Token(self, "control", 4)
+        self.tra_r_I = [0.0, 0.0, 5.0]
+        self.tra_q = toQuaternion(0.7, [0, 1, 0])
+        self.att_power = 2          # quad_model.py:210 squares the attitude error; the gym variant does not
+        self.dt_plant = None
+
+    # quad_model.py:35-119 -- all six parameters are numeric in every caller (quad_policy.py:37)
+    def initDyn(self, Jx=None, Jy=None, Jz=None, mass=None, l=None, c=None):
+        for name, v in (("Jx", Jx), ("Jy", Jy), ("Jz", Jz), ("mass", mass), ("l", l), ("c", c)):
+            if v is None:
+                raise ValueError(f"symbolic {name} is not supported: pass a number (the reference always does)")
+        self.Jx, self.Jy, self.Jz, self.mass, self.l, self.c = float(Jx), float(Jy), float(Jz), float(mass), float(l), float(c)
+        self.g = 9.78               # quad_model.py:37
+        self.u_m = np.array([[1, 1, 1, 1], [0, -self.l / 2, 0, self.l / 2], [-self.l / 2, 0, self.l / 2, 0],
+                             [self.c, -self.c, self.c, -self.c]])
+        self.f = _Token(self, "dynamics", 13)
+
+    # quad_model.py:121-198
+    def initCost(self, wrt=None, wqt=None, wrf=None, wvf=None, wqf=None, wwf=None, wthrust=0.5, goal_pos=[0, 9, 5],
+                 goal_velo=[0, 0, 0], goal_atti=[0, [1, 0, 0]]):
+        if any(w is None for w in (wrt, wqt, wrf, wvf, wqf, wwf)):
+            raise ValueError("symbolic cost weights are not supported: pass numbers (the reference always does)")
+        if float(wqf) != 0.0:
+            raise NotImplementedError("wqf != 0 (goal attitude cost) is not part of the accelerated path; "
+                                      "the reference fixes wqf=0 (quad_policy.py:38)")
+        if any(float(v) != 0.0 for v in goal_velo):
+            raise NotImplementedError("non-zero goal velocity is not part of the accelerated path (reference uses 0)")
+        self.wrt, self.wqt, self.wrf, self.wvf, self.wqf, self.wwf = map(float, (wrt, wqt, wrf, wvf, wqf, wwf))
+        self.wthrust = float(wthrust)
+        self.goal_r_I = np.asarray(goal_pos, dtype=float).reshape(3)
+        self.goal_q = toQuaternion(goal_atti[0], goal_atti[1])
+        self.thrust_cost = _Token(self, "thrust_cost")
+        self.goal_cost = _Token(self, "goal_cost")
+        self.final_cost = _Token(self, "final_cost")
+
+    # quad_model.py:200-213
+    def init_TraCost(self, tra_pos=[0, 0, 5], tra_atti=[0.7, [0, 1, 0]]):
+        self.tra_r_I = [float(v) for v in np.asarray(tra_pos, dtype=float).reshape(-1)[0:3]]
+        self.tra_q = toQuaternion(tra_atti[0], tra_atti[1])
+        self.tra_cost = _Token(self, "tra_cost")
+
+    # quad_model.py:215-219: explicit Euler plant used by main.py:35,108
+    def setDyn(self, dt):
+        self.dt_plant = float(dt)
+
+    def dyn_fn(self, state, control):
+        """x + dt*f(x,u) on the host (closed-loop plant of main.py:108); numpy, single state."""
+        if self.dt_plant is None:
+            raise RuntimeError("call setDyn(dt) first")
+        x = np.asarray(state, dtype=float).reshape(13)
+        u = np.asarray(control, dtype=float).reshape(4)
+        q0, q1, q2, q3 = x[6:10]
+        wx, wy, wz = x[10:13]
+        T = u.sum()
+        f = np.empty(13)
+        f[0:3] = x[3:6]
+        f[3] = T / self.mass * 2 * (q1 * q3 + q0 * q2)
+        f[4] = T / self.mass * 2 * (q2 * q3 - q0 * q1)
+        f[5] = T / self.mass * (1 - 2 * (q1 * q1 + q2 * q2)) - self.g
+        f[6] = 0.5 * (-wx * q1 - wy * q2 - wz * q3)
+        f[7] = 0.5 * (wx * q0 + wz * q2 - wy * q3)
+        f[8] = 0.5 * (wy * q0 - wz * q1 + wx * q3)
+        f[9] = 0.5 * (wz * q0 + wy * q1 - wx * q2)
+        Mx, My = (u[3] - u[1]) * self.l / 2, (u[2] - u[0]) * self.l / 2
+        Mz = (u[0] - u[1] + u[2] - u[3]) * self.c
+        f[10] = (Mx - (self.Jz - self.Jy) * wy * wz) / self.Jx
+        f[11] = (My - (self.Jx - self.Jz) * wx * wz) / self.Jy
+        f[12] = (Mz - (self.Jy - self.Jx) * wx * wy) / self.Jz
+        return x + self.dt_plant * f
+
+    # quad_model.py:239-276 (host version, used by the shim for `self.traj`; the kernels have their own)
+    def get_quadrotor_position(self, wing_len, state_traj):
+        X = np.asarray(state_traj, dtype=float).reshape(-1, 13)
+        a = wing_len * 0.5 / math.sqrt(2.0)
+        body = np.array([[a, a, 0.0], [-a, a, 0.0], [-a, -a, 0.0], [a, -a, 0.0]])
+        q0, q1, q2, q3 = X[:, 6], X[:, 7], X[:, 8], X[:, 9]
+        C = np.empty((X.shape[0], 3, 3))         # world->body direction cosine matrix, no normalisation
+        C[:, 0, 0] = 1 - 2 * (q2 * q2 + q3 * q3); C[:, 0, 1] = 2 * (q1 * q2 + q0 * q3); C[:, 0, 2] = 2 * (q1 * q3 - q0 * q2)
+        C[:, 1, 0] = 2 * (q1 * q2 - q0 * q3); C[:, 1, 1] = 1 - 2 * (q1 * q1 + q3 * q3); C[:, 1, 2] = 2 * (q2 * q3 + q0 * q1)
+        C[:, 2, 0] = 2 * (q1 * q3 + q0 * q2); C[:, 2, 1] = 2 * (q2 * q3 - q0 * q1); C[:, 2, 2] = 1 - 2 * (q1 * q1 + q2 * q2)
+        pos = np.empty((X.shape[0], 15))
+        pos[:, 0:3] = X[:, 0:3]
+        for r in range(4):
+            pos[:, 3 * (r + 1):3 * (r + 2)] = X[:, 0:3] + np.einsum("tji,j->ti", C, body[r])
+        return pos

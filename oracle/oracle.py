@@ -41,6 +41,7 @@ class Problem(C.Structure):
 class Solution(C.Structure):
     _fields_ = [
         ("X", C.c_double * ((NMAX + 1) * 13)), ("U", C.c_double * (NMAX * 4)), ("LAM", C.c_double * (NMAX * 13)),
+        ("XRAW", C.c_double * ((NMAX + 1) * 13)), ("URAW", C.c_double * (NMAX * 4)),
         ("ZL", C.c_double * (NMAX * 17 + 13)), ("ZU", C.c_double * (NMAX * 17 + 13)),
         ("cost", C.c_double), ("kkt_error", C.c_double), ("mu", C.c_double), ("obj_scale", C.c_double),
         ("dual_inf", C.c_double), ("constr_viol", C.c_double), ("compl_inf", C.c_double),
@@ -221,6 +222,7 @@ def _sol_dict(p, sol: Solution):
         "state_traj_opt": np.array(sol.X[: (N + 1) * 13]).reshape(N + 1, 13),
         "control_traj_opt": np.array(sol.U[: N * 4]).reshape(N, 4),
         "costate_traj_opt": np.array(sol.LAM[: N * 13]).reshape(N, 13),
+        "x_raw": np.array(sol.XRAW[: (N + 1) * 13]).reshape(N + 1, 13), "u_raw": np.array(sol.URAW[: N * 4]).reshape(N, 4),
         "zL": np.array(sol.ZL[: N * 17 + 13]), "zU": np.array(sol.ZU[: N * 17 + 13]),
         "cost": float(sol.cost), "status": int(sol.status), "iters": int(sol.iters), "nfact": int(sol.nfact),
         "nls": int(sol.nls), "nsoc": int(sol.nsoc), "kkt_error": float(sol.kkt_error), "mu": float(sol.mu),

@@ -722,7 +722,7 @@ static void build_rhs(ipm_t *s, double mu, rhs_t *r)
 }
 
 typedef struct { double theta, phi; } fentry;
-#define FILT_MAX 256
+#define FILT_MAX 32
 
 static int compare_le(double lhs, double rhs, double base)
 {   /* IPOPT Compare_le */
@@ -1102,9 +1102,11 @@ int se3o_solve(const se3o_params *p, const se3o_problem *pb, se3o_solution *sol)
             double v = s->x[k][i];
             if (k >= 1 && i >= 10) v = fmin(fmax(v, -p->w_bound), p->w_bound);
             sol->X[k * NX + i] = v;
+            sol->XRAW[k * NX + i] = s->x[k][i];
         }
     for (int k = 0; k < N; k++) {
         for (int j = 0; j < NU; j++) sol->U[k * NU + j] = fmin(fmax(s->u[k][j], p->u_lb), p->u_ub);
+        for (int j = 0; j < NU; j++) sol->URAW[k * NU + j] = s->u[k][j];
         for (int i = 0; i < NX; i++) sol->LAM[k * NX + i] = s->lam[k][i] / s->sf;   /* unscaled lam_g */
     }
     for (int k = 0; k <= N; k++)

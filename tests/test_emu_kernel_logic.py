@@ -1,0 +1,91 @@
+"""CPU tier: the CUDA solver source (csrc/se3mpc_core.cuh) compiled as a host warp emulation (tests/emu) against the
+oracle.  This exercises the kernel's control flow and arithmetic order without a GPU; the -m gpu tests run the
+real kernels through the C ABI."""
+import numpy as np
+import pytest
+
+from tests.common import flat_w, sample_scenarios
+
+
+def test_emulated_kernel_solution_matches_oracle(oracle, emu):
+    O, E = oracle, emu
+    p = O.default_params()
+    pe = E.params_from(p)
+    sc = sample_scenarios(6, 31)
+    for i in range(6):
+        pb = O.make_problem(sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], O.rd2quat(sc["tra_ang"][i]), sc["t"][i])
+        so = O.solve(p, pb)
+        se = E.solve(pe, sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], sc["tra_ang"][i], sc["t"][i])
+        assert so["status"] == 0 and se["status"] == 0
+        assert abs(so["cost"] - se["cost"]) <= 1e-6 * abs(so["cost"])                      # north_star: 1e-6 relative
+        assert np.abs(so["state_traj_opt"] - se["state_traj_opt"]).max() <= 1e-5           # north_star: 1e-5
+        assert np.abs(so["control_traj_opt"] - se["control_traj_opt"]).max() <= 1e-5
+        assert abs(so["iters"] - se["iters"]) <= 3
+
+
+def test_emulated_kernel_gym_variant_and_ulast(oracle, emu):
+    O, E = oracle, emu
+    p = O.default_params(att_power=1, u_ub=2.4)
+    pe = E.params_from(p)
+    sc = sample_scenarios(2, 32)
+    ul = np.array([1.0, 1.3, 0.9, 1.1])
+    for i in range(2):
+        pb = O.make_problem(sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], O.rd2quat(sc["tra_ang"][i]), sc["t"][i] + 0.04, ul)
+        so = O.solve(p, pb)
+        se = E.solve(pe, sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], sc["tra_ang"][i], sc["t"][i] + 0.04, ulast=ul)
+        assert abs(so["cost"] - se["cost"]) <= 1e-6 * abs(so["cost"])
+        assert np.abs(so["control_traj_opt"] - se["control_traj_opt"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("delta_w", [0.0, 50.0])
+def test_emulated_riccati_step_matches_oracle(oracle, emu, delta_w):
+    O, E = oracle, emu
+    p = O.default_params()
+    pe = E.params_from(p)
+    rng = np.random.default_rng(4)
+    sc = sample_scenarios(1, 33)
+    tq = O.rd2quat(sc["tra_ang"][0])
+    pb = O.make_problem(sc["x0"][0], sc["goal"][0], sc["tra_pos"][0], tq, sc["t"][0])
+    sol = O.solve(p, pb)
+    N = p.N
+    n, m = 17 * N + 13, 13 * N
+    w = flat_w(sol["x_raw"], sol["u_raw"])
+    w[13:] += rng.normal(0, 0.01, n - 13)
+    for k in range(N):
+        w[k * 17 + 13:k * 17 + 17] = np.clip(w[k * 17 + 13:k * 17 + 17], 0.01, 2.43)
+        w[(k + 1) * 17 + 10:(k + 1) * 17 + 13] = np.clip(w[(k + 1) * 17 + 10:(k + 1) * 17 + 13], -1.5, 1.5)
+    lam = sol["costate_traj_opt"].reshape(-1) * sol["obj_scale"] + rng.normal(0, 0.5, m)
+    zL, zU = rng.uniform(0.05, 1.5, n), rng.uniform(0.05, 1.5, n)
+    oko, dwo, lpo = O.kkt_step(p, pb, w, lam, zL, zU, 0.02, delta_w, sol["obj_scale"])
+    oke, dwe, lpe = E.kkt_step(pe, sc["goal"][0], sc["tra_pos"][0], tq, sc["t"][0], None, w, lam, zL, zU, 0.02, delta_w, sol["obj_scale"])
+    assert oko == oke
+    if oko:
+        assert np.abs(dwo - dwe).max() <= 1e-9 * max(1.0, np.abs(dwo).max())
+        assert np.abs(lpo - lpe).max() <= 1e-9 * max(1.0, np.abs(lpo).max())
+
+
+def test_emulated_reward_matches_oracle(oracle, emu):
+    O, E = oracle, emu
+    p = O.default_params()
+    pe = E.params_from(p)
+    from tests.test_oracle_kkt_reward import _random_traj
+    rng = np.random.default_rng(6)
+    sc = sample_scenarios(40, 34)
+    for i in range(40):
+        X = _random_traj(rng)
+        ro = O.reward(p, X, sc["gate"][i], sc["goal"][i])
+        re = E.reward(pe, X, sc["gate"][i], sc["goal"][i])
+        assert abs(ro[0] - re[0]) <= 1e-9 and abs(ro[1] - re[1]) <= 1e-12 and abs(ro[2] - re[2]) <= 1e-10 and ro[3] == re[3]
+
+
+def test_rd2quat(oracle, emu):
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        a = rng.normal(0, 0.5, 3)
+        assert np.allclose(oracle.rd2quat(a), emu.rd2quat(a), rtol=0, atol=1e-15)
+    assert np.allclose(emu.rd2quat(np.zeros(3)), [1, 0, 0, 0])
+
+
+def test_smem_and_slot_budget(emu):
+    # 4 warps/CTA x 4 CTAs/SM must fit the 227 KB of shared memory of an SM (csrc/se3mpc.cu launch configuration)
+    assert emu.lib().se3emu_smem_bytes() * 16 <= 227 * 1024
