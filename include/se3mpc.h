@@ -144,6 +144,10 @@ int se3mpc_sol_gradient_host(const se3mpc_params *p, int B, const double *x0, co
 /* frees the staging buffers the *_host entry points cache */
 void se3mpc_host_release(void);
 
+/* FP64 FMA-pipe peak probe (dependent-free DFMA chains on every SM): the denominator of the solver's roofline.
+ * Enqueues one launch; *flops_per_launch = FLOPs it performs (2 per FMA).  Time it with CUDA events. */
+int se3mpc_fp64_probe_device(int iters, double *sink, void *stream, double *flops_per_launch);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 long long se3mpc_launch_count(void);
 

@@ -40,10 +40,9 @@ struct KArgs {
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     se3::Ctx c;
-    c.sm = reinterpret_cast<se3::WarpSmem *>(smem_raw) + warp;
+    c.sm = reinterpret_cast<se3::WarpSmem *>(se3_smem_raw) + warp;
     c.ws = a.slots + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * se3::SLOT_DOUBLES;
     const int N = a.par.N;
 
@@ -164,6 +163,20 @@ __global__ void __launch_bounds__(256) se3mpc_collis_kernel(int B, int horizon, 
             if (co_out) co_out[pb] = co;
         }
     }
+}
+
+// FP64 FMA-pipe peak probe: 8 independent DFMA chains per thread (MEASURED_PEAKS.json has no fp64 entry)
+__global__ void __launch_bounds__(256) se3mpc_fp64_probe_kernel(int iters, double seed, double *sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
 }
 
 // quad_policy.py:98-112 over the 9 rewards of every sample
@@ -346,6 +359,18 @@ int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const d
     se3mpc_reward_kernel<<<grid, warps_per_cta * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches++;
     CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_fp64_probe_device(int iters, double *sink, void *stream, double *flops_per_launch)
+{
+    if (iters <= 0 || !sink) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    const int grid = num_sms() * 8;
+    se3mpc_fp64_probe_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, 1.0, sink);
+    g_launches++;
+    CK(cudaGetLastError());
+    if (flops_per_launch) *flops_per_launch = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
     return SE3MPC_OK;
 }
 

@@ -59,7 +59,7 @@ extern "C" int se3emu_kkt_step(const se3mpc_params *p, const double *goal, const
     Ctx c;
     c.sm = (WarpSmem *)calloc(1, sizeof(WarpSmem));
     c.ws = (double *)calloc(SLOT_DOUBLES, sizeof(double));
-    Prob &P = c.P;
+    Prob &P = c.sm->P;
     prob_from_params(*p, P);
     const int N = P.N;
     for (int i = 0; i < 3; i++) { P.goal[i] = goal[i]; P.ptra[i] = tra_pos[i]; }
@@ -67,7 +67,7 @@ extern "C" int se3emu_kkt_step(const se3mpc_params *p, const double *goal, const
     P.ttra = t_tra;
     att_form(tra_q, P.Nq, &P.s0);
     P.sf = obj_factor;
-    c.nfact = 0;
+    c.sm->nfact = 0;
     for (int s = 0; s <= N; s++) {
         for (int i = 0; i < 13; i++) row(c, R_X + i)[s] = w[s * 17 + i];
         for (int j = 0; j < 3; j++) { row(c, R_ZLW + j)[s] = zL[s * 17 + 10 + j]; row(c, R_ZUW + j)[s] = zU[s * 17 + 10 + j]; }
