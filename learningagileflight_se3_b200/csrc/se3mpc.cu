@@ -41,8 +41,12 @@ struct KArgs {
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTA-shared per-lane work table (identical for every warp), then one WarpSmem per warp
+    if (warp == 0) se3::make_lane_tab(lane, a.par, reinterpret_cast<se3::LaneTab *>(se3_smem_raw)[lane]);
+    __syncthreads();
     se3::Ctx c;
-    c.sm = reinterpret_cast<se3::WarpSmem *>(se3_smem_raw) + warp;
+    c.sm = reinterpret_cast<se3::WarpSmem *>(se3_smem_raw + se3::LTAB_BYTES) + warp;
+    c.lt = reinterpret_cast<const se3::LaneTab *>(se3_smem_raw);
     c.ws = a.slots + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * se3::SLOT_DOUBLES;
     const int N = a.par.N;
 
@@ -288,7 +292,7 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     if (status_override) a.status = status_override;
     a.slots = L.slots; a.ticket = L.ticket;
     CK(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), stream));
-    const size_t smem = sizeof(se3::WarpSmem) * WARPS_PER_CTA;
+    const size_t smem = se3::LTAB_BYTES + sizeof(se3::WarpSmem) * WARPS_PER_CTA;
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(se3mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     const int grid = L.nslots / WARPS_PER_CTA;

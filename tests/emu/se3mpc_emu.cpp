@@ -9,6 +9,15 @@
 
 using namespace se3;
 
+static LaneTab g_tab[32];
+static void make_ctx(Ctx &c, const se3mpc_params *p)
+{
+    c.sm = (WarpSmem *)calloc(1, sizeof(WarpSmem));
+    c.ws = (double *)calloc(SLOT_DOUBLES, sizeof(double));
+    for (int lane = 0; lane < 32; lane++) make_lane_tab(lane, *p, g_tab[lane]);
+    c.lt = g_tab;
+}
+
 static void make_instance(const double *x0, const double *goal, const double *tra_pos, const double *tra_ang, double t,
                           const double *ulast, int round_t, Instance &in)
 {
@@ -25,8 +34,7 @@ extern "C" int se3emu_solve(const se3mpc_params *p, const double *x0, const doub
                             double *LAM, double *cost, int *stats4, double *kkt_error)
 {
     Ctx c;
-    c.sm = (WarpSmem *)calloc(1, sizeof(WarpSmem));
-    c.ws = (double *)calloc(SLOT_DOUBLES, sizeof(double));
+    make_ctx(c, p);
     Instance in;
     make_instance(x0, goal, tra_pos, tra_ang, t, ulast, round_t, in);
     SolveStats st = ipm_solve(c, *p, in);
@@ -57,8 +65,7 @@ extern "C" int se3emu_kkt_step(const se3mpc_params *p, const double *goal, const
                                double *lam_plus)
 {
     Ctx c;
-    c.sm = (WarpSmem *)calloc(1, sizeof(WarpSmem));
-    c.ws = (double *)calloc(SLOT_DOUBLES, sizeof(double));
+    make_ctx(c, p);
     Prob &P = c.sm->P;
     prob_from_params(*p, P);
     const int N = P.N;
