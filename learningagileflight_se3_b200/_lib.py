@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libse3mpc.so")
+LIB_PATH = os.environ.get("SE3MPC_LIB") or os.path.join(CSRC, "libse3mpc.so")   # SE3MPC_LIB: tuning builds only
 
 
 class Se3MpcError(RuntimeError):

@@ -21,8 +21,14 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 4;
-constexpr int CTAS_PER_SM = 4;          // 16 resident warps (= problems) per SM; ~40 KB shared memory per CTA
+#ifndef SE3_WARPS_PER_CTA
+#define SE3_WARPS_PER_CTA 4
+#endif
+#ifndef SE3_CTAS_PER_SM
+#define SE3_CTAS_PER_SM 4
+#endif
+constexpr int WARPS_PER_CTA = SE3_WARPS_PER_CTA;
+constexpr int CTAS_PER_SM = SE3_CTAS_PER_SM;          // resident warps (= problems) per SM = product; ~12 KB shared memory per warp
 
 enum : int { MODE_SOLVE = 0, MODE_OBJECTIVE = 1, MODE_SOLGRAD = 2 };
 
@@ -42,7 +48,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTA-shared per-lane work table (identical for every warp), then one WarpSmem per warp
-    if (warp == 0) se3::make_lane_tab(lane, a.par, reinterpret_cast<se3::LaneTab *>(se3_smem_raw)[lane]);
+    if (warp == 0) se3::make_lane_tab(lane, reinterpret_cast<se3::LaneTab *>(se3_smem_raw)[lane]);
     __syncthreads();
     se3::Ctx c;
     c.sm = reinterpret_cast<se3::WarpSmem *>(se3_smem_raw + se3::LTAB_BYTES) + warp;

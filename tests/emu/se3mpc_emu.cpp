@@ -14,7 +14,7 @@ static void make_ctx(Ctx &c, const se3mpc_params *p)
 {
     c.sm = (WarpSmem *)calloc(1, sizeof(WarpSmem));
     c.ws = (double *)calloc(SLOT_DOUBLES, sizeof(double));
-    for (int lane = 0; lane < 32; lane++) make_lane_tab(lane, *p, g_tab[lane]);
+    for (int lane = 0; lane < 32; lane++) make_lane_tab(lane, g_tab[lane]);
     c.lt = g_tab;
 }
 
@@ -92,7 +92,7 @@ extern "C" int se3emu_kkt_step(const se3mpc_params *p, const double *goal, const
     init_AB(c);
     double th, ci;
     eval_constraints(c, &th, &ci);
-    int ok = riccati(c, SE3_MODE_EXACT, 1, delta_w, mu, R_C, R_DX, R_DU, R_LAMP);
+    int ok = riccati(c, SE3_MODE_EXACT, 1, 1, delta_w, mu, R_C, R_DX, R_DU, R_LAMP);
     for (int s = 0; s <= N; s++) {
         for (int i = 0; i < 13; i++) dw[s * 17 + i] = row(c, R_DX + i)[s];
         if (s < N) {
