@@ -2,7 +2,7 @@
 // se3mpc_core.cuh for the warp-cooperative interior-point solver.
 //
 // Kernels
-//   se3mpc_solve_kernel   persistent warps (16 per SM), one problem per warp at a time, problems handed out by an
+//   se3mpc_solve_kernel   persistent warps (8 per SM, 255 registers each), one problem per warp at a time, problems handed out by an
 //                         atomic ticket so that the very different iteration counts of the NLPs do not leave a tail.
 //                         modes: solve (OCSys.ocSolver), objective (solve + reward fused in the epilogue),
 //                         sol_gradient (9 perturbed objectives per sample, quad_policy.py:94-112).
@@ -25,7 +25,7 @@ namespace {
 #define SE3_WARPS_PER_CTA 4
 #endif
 #ifndef SE3_CTAS_PER_SM
-#define SE3_CTAS_PER_SM 4
+#define SE3_CTAS_PER_SM 2   // measured on B200 (profiles/README.md): 8 warps/SM with 255 registers beats 12 and 16 warps/SM
 #endif
 constexpr int WARPS_PER_CTA = SE3_WARPS_PER_CTA;
 constexpr int CTAS_PER_SM = SE3_CTAS_PER_SM;          // resident warps (= problems) per SM = product; ~12 KB shared memory per warp
