@@ -59,7 +59,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("SE3_SMI_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -195,6 +195,7 @@ def main():
     launches = se3.launch_count() - launches0
     clk = clocks.stop()
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    print(f"[rank {rank}] per-step ms: {[round(a.elapsed_time(b), 2) for a, b in ev]}", file=sys.stderr)
     conv = sum(int((r["status"] <= 1).sum().item()) for r in results)
     flops = sum(algorithmic_flops(r["iters"].cpu().numpy().astype(np.float64), r["nfact"].cpu().numpy().astype(np.float64),
                                   r["nls"].cpu().numpy().astype(np.float64)) for r in results)

@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -42,6 +43,7 @@ struct KArgs {
     double *kkt_error;
     double *slots;
     unsigned int *ticket;
+    const int32_t *order;      // longest-predicted-first processing order (or nullptr)
 };
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_
         if (lane == 0) pb = atomicAdd(a.ticket, 1u);
         pb = __shfl_sync(0xffffffffu, pb, 0);
         if (pb >= (unsigned)a.nprob) break;
+        if (a.order) pb = (unsigned)a.order[pb];
 
         // ---- instance (uniform registers) ----
         int src = (int)pb, variant = 0;
@@ -118,6 +121,61 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_
         }
         __syncwarp();
     }
+}
+
+// ---- longest-predicted-first ordering ------------------------------------------------------------------------------
+// The NLPs need 35..130 interior-point iterations; with more problems than resident warps the makespan is set by the
+// stragglers that start late.  A linear predictor of the factorisation count (fitted on 1500 synthetic scenarios,
+// correlation 0.69) buckets the problems; warps take tickets in descending-bucket order.  Results do not depend on the
+// order (every problem is solved by one warp with a fixed arithmetic order).
+constexpr int LPT_BUCKETS = 256;
+
+__device__ __forceinline__ int lpt_bucket(const KArgs &a, int pb)
+{
+    const int src = (a.mode == MODE_SOLGRAD) ? pb / 9 : pb;
+    const double *x0 = a.x0 + (size_t)src * 13, *g = a.goal + (size_t)src * 3, *tp = a.tra_pos + (size_t)src * 3;
+    const double *ta = a.tra_ang + (size_t)src * a.att_dim;
+    const double r0 = sqrt(x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2]);
+    const double dist = sqrt((x0[0] - g[0]) * (x0[0] - g[0]) + (x0[1] - g[1]) * (x0[1] - g[1]) + (x0[2] - g[2]) * (x0[2] - g[2]));
+    const double ntp = sqrt(tp[0] * tp[0] + tp[1] * tp[1] + tp[2] * tp[2]);
+    double nta;
+    if (a.att_dim == 3) nta = sqrt(ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2]);
+    else nta = sqrt(ta[1] * ta[1] + ta[2] * ta[2] + ta[3] * ta[3]) / fmax(fabs(ta[0]), 1e-3);     // tan(theta/2) from the quaternion
+    const double score = 16.6 + 3.12 * r0 + 77.3 * nta - 36.6 * ntp + 2.67 * dist;
+    int b = (int)score;
+    b = b < 0 ? 0 : (b > LPT_BUCKETS - 1 ? LPT_BUCKETS - 1 : b);
+    return LPT_BUCKETS - 1 - b;        // bucket 0 = predicted longest
+}
+
+__global__ void se3mpc_lpt_hist(const __grid_constant__ KArgs a, int32_t *hist, int32_t *key)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nprob) return;
+    const int b = lpt_bucket(a, i);
+    key[i] = b;
+    atomicAdd(&hist[b], 1);
+}
+
+__global__ void se3mpc_lpt_scan(int32_t *hist)
+{
+    __shared__ int32_t sh[LPT_BUCKETS];
+    const int t = threadIdx.x;
+    sh[t] = hist[t];
+    __syncthreads();
+    if (t == 0) {
+        int32_t run = 0;
+        for (int b = 0; b < LPT_BUCKETS; b++) { const int32_t c = sh[b]; sh[b] = run; run += c; }
+    }
+    __syncthreads();
+    hist[t] = sh[t];
+}
+
+__global__ void se3mpc_lpt_scatter(int nprob, int32_t *offs, const int32_t *key, int32_t *order)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nprob) return;
+    const int pos = atomicAdd(&offs[key[i]], 1);
+    order[pos] = i;
 }
 
 struct RArgs {
@@ -262,7 +320,7 @@ bool params_ok(const se3mpc_params *p)
 }
 
 // workspace: [ticket | pad to 256 B][aux doubles: nprob][aux int32: nprob][slots]
-struct WsLayout { unsigned int *ticket; double *aux_d; int32_t *aux_i; double *slots; int nslots; size_t bytes; };
+struct WsLayout { unsigned int *ticket; double *aux_d; int32_t *aux_i, *lpt_hist, *lpt_key, *lpt_order; double *slots; int nslots; size_t bytes; };
 
 WsLayout layout(void *ws, int nproblems)
 {
@@ -273,6 +331,12 @@ WsLayout layout(void *ws, int nproblems)
     L.aux_d = reinterpret_cast<double *>(b + off);
     off += ((size_t)nproblems * sizeof(double) + 255) / 256 * 256;
     L.aux_i = reinterpret_cast<int32_t *>(b + off);
+    off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
+    L.lpt_hist = reinterpret_cast<int32_t *>(b + off);
+    off += (size_t)LPT_BUCKETS * sizeof(int32_t);
+    L.lpt_key = reinterpret_cast<int32_t *>(b + off);
+    off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
+    L.lpt_order = reinterpret_cast<int32_t *>(b + off);
     off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
     L.slots = reinterpret_cast<double *>(b + off);
     L.nslots = slots_for(nproblems);
@@ -298,6 +362,17 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     if (status_override) a.status = status_override;
     a.slots = L.slots; a.ticket = L.ticket;
     CK(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), stream));
+    static const bool lpt_off = (getenv("SE3MPC_NO_LPT") != nullptr);      // A/B switch for profiling
+    if (nprob > L.nslots && !lpt_off) {     // more problems than resident warps: longest-predicted-first order
+        CK(cudaMemsetAsync(L.lpt_hist, 0, LPT_BUCKETS * sizeof(int32_t), stream));
+        const int tb = 256, nb = (nprob + tb - 1) / tb;
+        se3mpc_lpt_hist<<<nb, tb, 0, stream>>>(a, L.lpt_hist, L.lpt_key);
+        se3mpc_lpt_scan<<<1, LPT_BUCKETS, 0, stream>>>(L.lpt_hist);
+        se3mpc_lpt_scatter<<<nb, tb, 0, stream>>>(nprob, L.lpt_hist, L.lpt_key, L.lpt_order);
+        g_launches += 3;
+        CK(cudaGetLastError());
+        a.order = L.lpt_order;
+    }
     const size_t smem = se3::LTAB_BYTES + sizeof(se3::WarpSmem) * WARPS_PER_CTA;
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(se3mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });

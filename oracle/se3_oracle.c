@@ -1057,6 +1057,8 @@ int se3o_solve(const se3o_params *p, const se3o_problem *pb, se3o_solution *sol)
         }
         (void)ddx; (void)ddu;
         if (!accepted) { status = 3; break; }
+        if (getenv("SE3O_VERBOSE3"))
+            fprintf(stderr, "   ls: alpha_max=%.3e alpha=%.3e alpha_z=%.3e ntrial_total=%d gphid=%.3e theta_k=%.3e theta_t? nfilt=%d\n", alpha_max, alpha, alpha_z, nls, gphid, theta_k, nfilt);
 
         /* filter augmentation (uses the original alpha_test / direction) */
         {
