@@ -12,7 +12,8 @@ using namespace se3;
 static LaneTab g_tab[32];
 static void make_ctx(Ctx &c, const se3mpc_params *p)
 {
-    c.sm = (WarpSmem *)calloc(1, sizeof(WarpSmem));
+    c.sm = (WarpSmem *)malloc(sizeof(WarpSmem));
+    memset(c.sm, 0xFF, sizeof(WarpSmem));      // NaN pattern: shared memory is not zero on the GPU either
     c.ws = (double *)calloc(SLOT_DOUBLES, sizeof(double));
     for (int lane = 0; lane < 32; lane++) make_lane_tab(lane, g_tab[lane]);
     c.lt = g_tab;
