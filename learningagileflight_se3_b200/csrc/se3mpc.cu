@@ -26,10 +26,10 @@ namespace {
 #define SE3_WARPS_PER_CTA 4
 #endif
 #ifndef SE3_CTAS_PER_SM
-#define SE3_CTAS_PER_SM 2   // measured on B200 (profiles/README.md): 8 warps/SM with 255 registers beats 12 and 16 warps/SM
+#define SE3_CTAS_PER_SM 3   // measured on B200 (profiles/README.md): 12 warps/SM (168 registers); the GPC instruction cache, not occupancy, bounds the kernel
 #endif
 constexpr int WARPS_PER_CTA = SE3_WARPS_PER_CTA;
-constexpr int CTAS_PER_SM = SE3_CTAS_PER_SM;          // resident warps (= problems) per SM = product; ~12 KB shared memory per warp
+constexpr int CTAS_PER_SM = SE3_CTAS_PER_SM;          // resident warps (= problems) per SM = product; 13 KB shared memory per warp
 
 enum : int { MODE_SOLVE = 0, MODE_OBJECTIVE = 1, MODE_SOLGRAD = 2 };
 
