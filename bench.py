@@ -11,7 +11,7 @@ se3mpc_objective launch.  Inputs are synthetic (the reference's 
 
 Prints ONE JSON line.  `value` = converged solves/s with inputs resident in HBM (CUDA events on the launching
 stream, max over ranks); `e2e` = the same through the host-buffer C ABI (pinned host numpy in, host numpy out);
-`roofline` = the solver kernel against the measured FP64 FMA-pipe peak (measured live by a DFMA probe kernel since
+`roofline` = the solver kernel against the FP64 tensor/FMA peak (measured live by a DMMA probe kernel since
 MEASURED_PEAKS.json carries no fp64 figure), `roofline_reward` = the stand-alone reward kernel against measured
 HBM bandwidth; `cpu_baseline` = the CPU oracle ("port": restated fp64 IPM, NOT CasADi/IPOPT, which is not
 installable offline) on all host cores over a bounded sample.
@@ -43,6 +43,8 @@ W_FACT = N_H * 8267.0
 W_SOLVE = N_H * 1124.0
 W_EVAL = N_H * 600.0
 W_LS = N_H * 150.0
+# DRAM bytes per problem of se3mpc_solve_kernel from the committed ncu capture (profiles/README.md): slot traffic (records, factors)
+NCU_DRAM_BYTES_PER_PROBLEM = 32.8e6
 
 
 def algorithmic_flops(iters, nfact, nls):
@@ -246,14 +248,16 @@ def main():
         for _ in range(5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            L.se3mpc_fp64_probe_device(1 << 15, C.c_void_p(sink.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(fl))
+            L.se3mpc_fp64_probe_device(1 << 13, C.c_void_p(sink.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(fl))
             b.record(stream)
             torch.cuda.synchronize(dev)
             best = max(best, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
         achieved = flops / world / (t_ms * 1e-3) / 1e12 if world > 1 else flops / (t_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp64_fma", "kernel": "se3mpc_solve_kernel", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
-                    "frac": achieved / best if best else None, "traffic": None,
-                    "peak_source": "measured live: DFMA probe kernel (MEASURED_PEAKS.json has no fp64 figure)",
+        roofline = {"bound": "tensor", "kernel": "se3mpc_solve_kernel", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
+                    "frac": achieved / best if best else None, "traffic": NCU_DRAM_BYTES_PER_PROBLEM * B,
+                    "pipe": "FP64 tensor (DMMA.8x8x4) + FP64 FMA: same 16 FMA/clk/SMSP datapath",
+                    "peak_source": "measured live: FP64 DMMA probe kernel (MEASURED_PEAKS.json has only the bf16 tensor figure; this path computes in f64)",
+                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 4096-problem launch (profiles/), scaled per problem",
                     "flops_per_step": flops / K / world, "model": "SURVEY.md 8(d): n_fact*W_fact + n_iter*(W_solve+W_eval) + n_ls*W_ls per problem"}
         # stand-alone reward kernel (HBM bound): 5304+120 B read + 32 B written per trajectory
         NB = 1 << 18

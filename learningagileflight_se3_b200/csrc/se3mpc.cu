@@ -233,17 +233,22 @@ __global__ void __launch_bounds__(256) se3mpc_collis_kernel(int B, int horizon, 
     }
 }
 
-// FP64 FMA-pipe peak probe: 8 independent DFMA chains per thread (MEASURED_PEAKS.json has no fp64 entry)
+// FP64 peak probe: 8 independent DMMA.8x8x4 accumulator chains per warp (the instruction the factor sweep issues; on B200 the
+// FP64 tensor rate is 37 TFLOP/s, the DFMA rate 34 TFLOP/s -- profiles/micro/dmma_probe.cu).  MEASURED_PEAKS.json has no fp64 entry.
 __global__ void __launch_bounds__(256) se3mpc_fp64_probe_kernel(int iters, double seed, double *sink)
 {
-    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 0.999999, c = 1e-9;
-#pragma unroll 4
-    for (int i = 0; i < iters; i++) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = seed + threadIdx.x + i; c[i][1] = seed - i; }
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
     }
-    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r += c[i][0] + c[i][1];
     if (r == 123.456) sink[0] = r;
 }
 
@@ -455,7 +460,7 @@ int se3mpc_fp64_probe_device(int iters, double *sink, void *stream, double *flop
     se3mpc_fp64_probe_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, 1.0, sink);
     g_launches++;
     CK(cudaGetLastError());
-    if (flops_per_launch) *flops_per_launch = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+    if (flops_per_launch) *flops_per_launch = 512.0 * 8.0 * (double)iters * 8.0 * (double)grid;      // 512 flop per DMMA, 8 chains, 8 warps per CTA
     return SE3MPC_OK;
 }
 
