@@ -128,6 +128,17 @@ int se3mpc_sol_gradient_device(const se3mpc_params *p, int B, const double *x0, 
                                const double *tra_pos, const double *tra_ang, const double *t, const double *ulast,
                                double *out, int32_t *status9, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- moving-gate closed loop (main.py:65-116), one thread per episode ----
+ * se3mpc_gate_frame: gate(gate[b]).translate(t[b] velo[b]); .rotate_y(t[b] w[b])  (quad_model.py:686-700, 720-729), then the
+ *   DNN-2 input packing of main.py:86-94 (same as quad_moving.py:35-42):
+ *   inputs18[b] = [gate.transform(state[b]) (13, quad_model.py:793-810: scipy Rotation round trip re-stated) |
+ *                  gate.t_final(final_point[b]) (3) | width | pitch];  gate_pred[B][12] (optional) = the predicted corners.
+ * se3mpc_plant_step: state[b] <- nsteps explicit Euler steps of quad_model.py:86-119 with step dt and the control u[b] held
+ *   (main.py:108 with uav1.setDyn(0.01), main.py:35; 10 steps per MPC tick, main.py:76). state is updated in place. */
+int se3mpc_gate_frame_device(int B, const double *gate, const double *velo, const double *w, const double *t,
+                             const double *state, const double *final_point, double *inputs18, double *gate_pred, void *stream);
+int se3mpc_plant_step_device(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state, void *stream);
+
 /* Host-buffer variants: same semantics, HOST pointers, synchronous (H2D + kernels + D2H inside). */
 int se3mpc_solve_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *tra_pos,
                       const double *tra_att, int att_dim, const double *t, const double *ulast, int round_t,
@@ -135,6 +146,9 @@ int se3mpc_solve_host(const se3mpc_params *p, int B, const double *x0, const dou
 int se3mpc_reward_host(const se3mpc_params *p, int B, const double *X, const double *gate, const double *goal,
                        double *reward, double *collision, double *path, int32_t *co);
 int se3mpc_collis_det_host(int B, int horizon, const double *V, const double *gate, double *score, int32_t *co);
+int se3mpc_gate_frame_host(int B, const double *gate, const double *velo, const double *w, const double *t, const double *state,
+                           const double *final_point, double *inputs18, double *gate_pred);
+int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state);
 int se3mpc_objective_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *gate,
                           const double *tra_pos, const double *tra_ang, const double *t, const double *ulast,
                           double *reward, double *X, double *U, double *cost, const se3mpc_stats *stats);

@@ -48,6 +48,7 @@ EXPORTS = [
     "se3mpc_solve_device", "se3mpc_reward_device", "se3mpc_collis_det_device", "se3mpc_objective_device",
     "se3mpc_sol_gradient_device", "se3mpc_solve_host", "se3mpc_reward_host", "se3mpc_collis_det_host",
     "se3mpc_objective_host", "se3mpc_sol_gradient_host", "se3mpc_host_release", "se3mpc_launch_count", "se3mpc_fp64_probe_device",
+    "se3mpc_gate_frame_device", "se3mpc_gate_frame_host", "se3mpc_plant_step_device", "se3mpc_plant_step_host",
 ]
 
 
@@ -93,6 +94,12 @@ def lib():
     L.se3mpc_reward_host.argtypes = [pp, ci, vp, vp, vp, vp, vp, vp, vp]
     L.se3mpc_objective_host.argtypes = [pp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sp]
     L.se3mpc_sol_gradient_host.argtypes = [pp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.se3mpc_gate_frame_device.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.se3mpc_gate_frame_host.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.se3mpc_plant_step_device.argtypes = [pp, ci, C.c_double, ci, vp, vp, vp]
+    L.se3mpc_plant_step_host.argtypes = [pp, ci, C.c_double, ci, vp, vp]
+    for f in ("se3mpc_gate_frame_device", "se3mpc_gate_frame_host", "se3mpc_plant_step_device", "se3mpc_plant_step_host"):
+        getattr(L, f).restype = ci
     for f in ("se3mpc_collis_det_device", "se3mpc_collis_det_host", "se3mpc_solve_device", "se3mpc_reward_device", "se3mpc_objective_device", "se3mpc_sol_gradient_device",
               "se3mpc_solve_host", "se3mpc_reward_host", "se3mpc_objective_host", "se3mpc_sol_gradient_host"):
         getattr(L, f).restype = ci

@@ -178,6 +178,35 @@ __global__ void se3mpc_lpt_scatter(int nprob, int32_t *offs, const int32_t *key,
     order[pos] = i;
 }
 
+// ---- moving-gate closed loop (main.py:65-116): one thread per episode -------------------------------------------------
+__global__ void se3mpc_gate_frame_kernel(int B, const double *gate, const double *velo, const double *w, const double *t,
+                                         const double *state, const double *fin, double *inputs18, double *gate_pred)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double g[12], v[3], x[13], f[3], out[18], gp[12];
+    for (int i = 0; i < 12; i++) g[i] = gate[(size_t)b * 12 + i];
+    for (int i = 0; i < 3; i++) { v[i] = velo[(size_t)b * 3 + i]; f[i] = fin[(size_t)b * 3 + i]; }
+    for (int i = 0; i < 13; i++) x[i] = state[(size_t)b * 13 + i];
+    se3::gate_frame(g, v, w[b], t[b], x, f, out, gate_pred ? gp : nullptr);
+    for (int i = 0; i < 18; i++) inputs18[(size_t)b * 18 + i] = out[i];
+    if (gate_pred)
+        for (int i = 0; i < 12; i++) gate_pred[(size_t)b * 12 + i] = gp[i];
+}
+
+__global__ void se3mpc_plant_step_kernel(const __grid_constant__ se3mpc_params par, int B, double dt, int nsteps, const double *u, double *state)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    se3::Prob P;
+    se3::prob_from_params(par, P);
+    double x[13], uu[4];
+    for (int i = 0; i < 13; i++) x[i] = state[(size_t)b * 13 + i];
+    for (int j = 0; j < 4; j++) uu[j] = u[(size_t)b * 4 + j];
+    se3::plant_steps(P, dt, nsteps, uu, x);
+    for (int i = 0; i < 13; i++) state[(size_t)b * 13 + i] = x[i];
+}
+
 struct RArgs {
     se3mpc_params par;
     int B;
@@ -698,6 +727,80 @@ int se3mpc_collis_det_host(int B, int horizon, const double *V, const double *ga
     if (rc != SE3MPC_OK) return rc;
     CK(cudaMemcpyAsync(score, d_s, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
     if (co) CK(cudaMemcpyAsync(co, d_co, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SE3MPC_OK;
+}
+
+int se3mpc_gate_frame_device(int B, const double *gate, const double *velo, const double *w, const double *t, const double *state,
+                             const double *final_point, double *inputs18, double *gate_pred, void *stream)
+{
+    if (B < 0 || !gate || !velo || !w || !t || !state || !final_point || !inputs18) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    se3mpc_gate_frame_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(B, gate, velo, w, t, state, final_point, inputs18, gate_pred);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_plant_step_device(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !(dt > 0) || nsteps < 0 || !u || !state) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0 || nsteps == 0) return SE3MPC_OK;
+    se3mpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, B, dt, nsteps, u, state);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_gate_frame_host(int B, const double *gate, const double *velo, const double *w, const double *t, const double *state,
+                           const double *final_point, double *inputs18, double *gate_pred)
+{
+    if (B < 0 || !gate || !velo || !w || !t || !state || !final_point || !inputs18) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = g_in.ensure(pad((size_t)B * 12 * 8) + 2 * pad((size_t)B * 3 * 8) + 2 * pad((size_t)B * 8) + pad((size_t)B * 13 * 8))) != SE3MPC_OK) return rc;
+    if ((rc = g_out.ensure(pad((size_t)B * 18 * 8) + pad((size_t)B * 12 * 8))) != SE3MPC_OK) return rc;
+    Arena ai{static_cast<unsigned char *>(g_in.p)}, ao{static_cast<unsigned char *>(g_out.p)};
+    double *d_g = ai.take<double>((size_t)B * 12), *d_v = ai.take<double>((size_t)B * 3), *d_f = ai.take<double>((size_t)B * 3);
+    double *d_w = ai.take<double>(B), *d_t = ai.take<double>(B), *d_x = ai.take<double>((size_t)B * 13);
+    double *d_o = ao.take<double>((size_t)B * 18), *d_gp = ao.take<double>((size_t)B * 12);
+    cudaStream_t s = g_stream;
+    CK(cudaMemcpyAsync(d_g, gate, (size_t)B * 12 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_v, velo, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_f, final_point, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_w, w, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_t, t, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_x, state, (size_t)B * 13 * 8, cudaMemcpyHostToDevice, s));
+    rc = se3mpc_gate_frame_device(B, d_g, d_v, d_w, d_t, d_x, d_f, d_o, gate_pred ? d_gp : nullptr, s);
+    if (rc != SE3MPC_OK) return rc;
+    CK(cudaMemcpyAsync(inputs18, d_o, (size_t)B * 18 * 8, cudaMemcpyDeviceToHost, s));
+    if (gate_pred) CK(cudaMemcpyAsync(gate_pred, d_gp, (size_t)B * 12 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SE3MPC_OK;
+}
+
+int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state)
+{
+    if (!params_ok(p) || B < 0 || !(dt > 0) || nsteps < 0 || !u || !state) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0 || nsteps == 0) return SE3MPC_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = g_in.ensure(pad((size_t)B * 4 * 8))) != SE3MPC_OK) return rc;
+    if ((rc = g_out.ensure(pad((size_t)B * 13 * 8))) != SE3MPC_OK) return rc;
+    double *d_u = static_cast<double *>(g_in.p), *d_x = static_cast<double *>(g_out.p);
+    cudaStream_t s = g_stream;
+    CK(cudaMemcpyAsync(d_u, u, (size_t)B * 4 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_x, state, (size_t)B * 13 * 8, cudaMemcpyHostToDevice, s));
+    rc = se3mpc_plant_step_device(p, B, dt, nsteps, d_u, d_x, s);
+    if (rc != SE3MPC_OK) return rc;
+    CK(cudaMemcpyAsync(state, d_x, (size_t)B * 13 * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return SE3MPC_OK;
 }

@@ -61,7 +61,7 @@ def _stats(B, device):
 
 
 def solve(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Optional[Params] = None,
-          want_traj=True, want_costate=True):
+          want_traj=True, want_costate=True, want_state=True):
     """OCSys.ocSolver for a batch (quad_OC.py:104-212).  Returns dict of device tensors.
 
     tra_ang is [B,3] (the planner's Rodrigues-like vector, converted on the device) or [B,4] (traversal quaternion)."""
@@ -71,7 +71,7 @@ def solve(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Opti
     att_dim = 4 if tra_ang.numel() == 4 * B else 3
     x0, goal, tra_pos, tra_ang, t = _c(x0, (B, 13)), _c(goal, (B, 3)), _c(tra_pos, (B, 3)), _c(tra_ang, (B, att_dim)), _c(t, (B,))
     ulast = _c(ulast, (B, 4))
-    X = torch.empty((B, N + 1, 13), dtype=torch.float64, device=dev) if want_traj else None
+    X = torch.empty((B, N + 1, 13), dtype=torch.float64, device=dev) if (want_traj and want_state) else None
     U = torch.empty((B, N, 4), dtype=torch.float64, device=dev) if want_traj else None
     LAM = torch.empty((B, N, 13), dtype=torch.float64, device=dev) if want_costate else None
     cost = torch.empty(B, dtype=torch.float64, device=dev)
@@ -242,6 +242,63 @@ def sol_gradient_host(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: O
                                              _np_ptr(t), _np_ptr(ulast), _np_ptr(out), C.c_void_p(st9.ctypes.data))
     _lib.check(rc, "se3mpc_sol_gradient_host")
     return out, st9
+
+
+# ---- moving-gate closed loop (main.py:65-116) ------------------------------------------------------------------
+def gate_frame(gate, velo, w, t, state, final_point, want_gate=False):
+    """DNN-2 inputs for the gate predicted t seconds ahead (main.py:86-94, quad_moving.py:35-42), device tensors.
+    gate[B,12], velo[B,3], w[B], t[B], state[B,13], final_point[B,3] -> inputs18[B,18] (and the predicted corners [B,12])."""
+    _require_cuda(gate, velo, w, t, state, final_point)
+    B, dev = state.reshape(-1, 13).shape[0], state.device
+    gate, velo, w, t = _c(gate, (B, 12)), _c(velo, (B, 3)), _c(w, (B,)), _c(t, (B,))
+    state, final_point = _c(state, (B, 13)), _c(final_point, (B, 3))
+    out = torch.empty(B, 18, dtype=torch.float64, device=dev)
+    gp = torch.empty(B, 12, dtype=torch.float64, device=dev) if want_gate else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().se3mpc_gate_frame_device(B, _ptr(gate), _ptr(velo), _ptr(w), _ptr(t), _ptr(state), _ptr(final_point), _ptr(out), _ptr(gp),
+                                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_gate_frame_device")
+    return (out, gp) if want_gate else out
+
+
+def plant_step(state, u, dt=0.01, nsteps=1, params: Optional[Params] = None):
+    """nsteps explicit Euler steps of the plant with the control held (main.py:108); returns a NEW state tensor [B,13]."""
+    _require_cuda(state, u)
+    p = params or default_params()
+    B, dev = state.reshape(-1, 13).shape[0], state.device
+    x = state.reshape(B, 13).contiguous().clone()
+    u = _c(u, (B, 4))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().se3mpc_plant_step_device(C.byref(p), B, float(dt), int(nsteps), _ptr(u), _ptr(x),
+                                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_plant_step_device")
+    return x
+
+
+def gate_frame_host(gate, velo, w, t, state, final_point, want_gate=False):
+    """Host-buffer variant of gate_frame (numpy in, numpy out)."""
+    state = _np(state, (-1, 13))
+    B = state.shape[0]
+    gate, velo, final_point = _np(gate, (B, 12)), _np(velo, (B, 3)), _np(final_point, (B, 3))
+    w = _np(np.broadcast_to(np.asarray(w, dtype=np.float64), (B,)), (B,))
+    t = _np(np.broadcast_to(np.asarray(t, dtype=np.float64), (B,)), (B,))
+    out = np.empty((B, 18))
+    gp = np.empty((B, 12)) if want_gate else None
+    rc = _lib.lib().se3mpc_gate_frame_host(B, _np_ptr(gate), _np_ptr(velo), _np_ptr(w), _np_ptr(t), _np_ptr(state), _np_ptr(final_point),
+                                           _np_ptr(out), _np_ptr(gp))
+    _lib.check(rc, "se3mpc_gate_frame_host")
+    return (out, gp) if want_gate else out
+
+
+def plant_step_host(state, u, dt=0.01, nsteps=1, params: Optional[Params] = None):
+    """Host-buffer variant of plant_step."""
+    p = params or default_params()
+    x = np.array(_np(state, (-1, 13)), copy=True)
+    B = x.shape[0]
+    u = _np(u, (B, 4))
+    rc = _lib.lib().se3mpc_plant_step_host(C.byref(p), B, float(dt), int(nsteps), _np_ptr(u), _np_ptr(x))
+    _lib.check(rc, "se3mpc_plant_step_host")
+    return x
 
 
 # ---- torch custom ops: torch.ops.se3mpc.{solve,reward,objective,sol_gradient} (CUDA dispatch key only) ------

@@ -123,3 +123,76 @@ class Quadrotor:
         for r in range(4):
             pos[:, 3 * (r + 1):3 * (r + 2)] = X[:, 0:3] + np.einsum("tji,j->ti", C, body[r])
         return pos
+
+
+class gate:
+    """Gate kinematics with the reference's interface (quad_model.py:671-815): 4x3 corner array, centroid, I_G, translate /
+    rotate_y / translate_out / rotate_y_out / move / transform / t_final.  The bookkeeping methods are tiny host-side numpy (they are
+    host-side in the reference too); `transform` and `t_final` -- the per-tick part of main.py:86-94 -- run on the GPU through
+    ops.gate_frame_host for the gate as it stands (velo = 0, t = 0).  Batched callers use ops.gate_frame directly."""
+
+    def __init__(self, gate_point=None):
+        self.gate_point = np.array(gate_point, dtype=float).reshape(4, 3)
+        self._refresh(transposed=True)          # quad_model.py:684 stores [ax ay az]^T in __init__, the rows elsewhere
+
+    def _refresh(self, transposed=False):
+        gp = self.gate_point
+        self.centroid = np.array([np.mean(gp[:, 0]), np.mean(gp[:, 1]), np.mean(gp[:, 2])])
+        az = np.array([0.0, 0.0, 1.0])
+        n = np.cross(gp[1] - gp[0], gp[2] - gp[1])
+        ay = n / np.sqrt(np.sum(n * n))
+        ax = np.cross(ay, az)
+        self.ay = ay
+        self.I_G = np.array([ax, ay, az]).T if transposed else np.array([ax, ay, az])
+
+    def rotate_y_out(self, angle):
+        c, s = math.cos(angle), math.sin(angle)
+        rel = self.gate_point - self.centroid
+        out = rel.copy()
+        out[:, 0] = c * rel[:, 0] - s * rel[:, 2]
+        out[:, 2] = s * rel[:, 0] + c * rel[:, 2]
+        return out + self.centroid
+
+    def rotate_y(self, angle):
+        self.gate_point = self.rotate_y_out(angle)
+        self._refresh()
+
+    def translate_out(self, displace):
+        return self.gate_point + np.asarray(displace, dtype=float).reshape(3)
+
+    def translate(self, displace):
+        self.gate_point = self.translate_out(displace)
+        self._refresh()
+
+    def move(self, T=5, dt=0.01, v=[0, 0, 0], w=0, rng=None):
+        """quad_model.py:769-790: corner trajectory [T/dt+1, 4, 3] and per-step velocity (clipped Gaussian noise, sigma 0.1).
+        `rng`: numpy Generator (the reference draws from the global numpy state; pass np.random for that behaviour)."""
+        rng = np.random if rng is None else rng
+        gp = self.gate_point.copy()
+        velo = np.asarray(v, dtype=float)
+        moves, V = [gp.copy()], [velo.copy()]
+        c, s = math.cos(dt * w), math.sin(dt * w)
+        for _ in range(int(T / dt)):
+            noise = np.clip(rng.normal(0, 0.1, 3), -0.1, 0.1)
+            cen = np.array([np.mean(gp[:, 0]), np.mean(gp[:, 1]), np.mean(gp[:, 2])])
+            rel = gp - cen
+            out = rel.copy()
+            out[:, 0] = c * rel[:, 0] - s * rel[:, 2]
+            out[:, 2] = s * rel[:, 0] + c * rel[:, 2]
+            gp = out + cen + dt * (velo + noise)
+            moves.append(gp.copy()); V.append(velo + noise)
+        return np.array(moves), np.array(V)
+
+    def _frame_inputs(self, state, final_point):
+        from . import ops
+        z3 = np.zeros((1, 3))
+        return ops.gate_frame_host(self.gate_point.reshape(1, 12), z3, np.zeros(1), np.zeros(1), np.asarray(state, float).reshape(1, 13),
+                                   np.asarray(final_point, float).reshape(1, 3))[0]
+
+    def transform(self, inertial_state):
+        """World-frame state -> gate-frame state (quad_model.py:793-810), computed by se3mpc_gate_frame (rows-form I_G, i.e. the
+        frame after translate / rotate_y, which is the only one the reference calls transform() in)."""
+        return self._frame_inputs(inertial_state, np.zeros(3))[0:13]
+
+    def t_final(self, final_point):
+        return self._frame_inputs(np.array([0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 0, 0]), final_point)[13:16]

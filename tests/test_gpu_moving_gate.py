@@ -1,0 +1,134 @@
+"""GPU tier, SURVEY.md 8(f) rank 1-2: the moving-gate closed loop of main.py / quad_moving.py through the C ABI, against the
+reference-generated golden fixture (tests/golden/gate_frame.npz) and the CPU oracle (oracle/gate_oracle.py, oracle/oracle.py)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "gate_frame.npz")
+
+
+def _torch_net(d, dev):
+    import torch
+    W1, b1, W2, b2 = (torch.as_tensor(d[k], dtype=torch.float64, device=dev) for k in ("W1", "b1", "W2", "b2"))
+
+    def f(x):
+        y = torch.tanh(x @ W1.T + b1) @ W2.T + b2
+        y = y.clone()
+        y[:, 6] = 2.0 + 1.5 * torch.tanh(0.5 * y[:, 6])
+        return y
+    return f
+
+
+def _np_net(d):
+    def f(x):
+        y = d["W2"] @ np.tanh(d["W1"] @ np.asarray(x, float) + d["b1"]) + d["b2"]
+        y[6] = 2.0 + 1.5 * math.tanh(0.5 * y[6])
+        return y
+    return f
+
+
+def test_gate_frame_matches_reference_golden_host_and_device():
+    import torch
+    from learningagileflight_se3_b200 import ops
+    d = np.load(GOLD)
+    out, gp = ops.gate_frame_host(d["gates"], d["velo"], d["w"], d["t"], d["state"], d["final"], want_gate=True)
+    assert np.abs(out - d["inputs"]).max() <= 1e-12                     # bit-level agreement up to libm vs CUDA sin/cos/atan
+    dev = torch.device("cuda", 0)
+    tt = lambda k: torch.as_tensor(d[k], dtype=torch.float64, device=dev)  # noqa: E731
+    out_d, gp_d = ops.gate_frame(tt("gates"), tt("velo"), tt("w"), tt("t"), tt("state"), tt("final"), want_gate=True)
+    assert np.array_equal(out_d.cpu().numpy(), out) and np.array_equal(gp_d.cpu().numpy(), gp)      # host ABI == device ABI
+    from oracle import gate_oracle as G
+    for i in range(8):
+        g, _, _ = G.predict_gate(d["gates"][i], d["velo"][i], d["w"][i], d["t"][i])
+        assert np.abs(gp[i].reshape(4, 3) - g).max() <= 1e-12
+    assert ops.gate_frame_host(np.zeros((0, 12)), np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros((0, 13)), np.zeros((0, 3))).shape == (0, 18)
+
+
+def test_plant_step_matches_oracle():
+    from learningagileflight_se3_b200 import ops
+    from oracle import gate_oracle as G
+    rng = np.random.default_rng(5)
+    B = 37
+    x = rng.normal(0, 1, (B, 13)); u = rng.uniform(0, 2.44, (B, 4))
+    for n in (1, 10):
+        got = ops.plant_step_host(x, u, 0.01, n)
+        ref = np.stack([G.plant_steps(x[i], u[i], 0.01, n) for i in range(B)])
+        assert np.abs(got - ref).max() <= 1e-12
+    assert np.array_equal(ops.plant_step_host(x, u, 0.01, 0), x)
+
+
+def test_traversal_time_fixed_point_batched_and_reference_signature():
+    import torch
+    from learningagileflight_se3_b200 import quad_moving
+    from learningagileflight_se3_b200.quad_model import gate
+    from oracle import gate_oracle as G
+    d = np.load(GOLD)
+    dev = torch.device("cuda", 0)
+    m = d["t_fix"].shape[0]
+    tt = lambda k: torch.as_tensor(d[k][:m], dtype=torch.float64, device=dev)  # noqa: E731
+    t1, iters = quad_moving.traversal_time(_torch_net(d, dev), tt("state"), tt("final"), tt("gates"), tt("velo"), tt("w"))
+    assert np.abs(t1.cpu().numpy() - d["t_fix"]).max() <= 1e-9           # golden: the reference's own quad_moving.solver
+    net = _np_net(d)
+    for i in range(4):
+        _, it = G.traversal_time(net, d["state"][i], d["final"][i], d["gates"][i], d["velo"][i], d["w"][i])
+        assert int(iters[i]) == it                                        # each episode stops where its own while-loop would
+        t = quad_moving.solver(net, d["state"][i], d["final"][i], gate(d["gates"][i].reshape(4, 3)), d["velo"][i], d["w"][i])
+        assert abs(t - d["t_fix"][i]) <= 1e-9
+
+
+def test_gate_mirror_class_transform_and_t_final():
+    from learningagileflight_se3_b200.quad_model import gate
+    d = np.load(GOLD)
+    for i in range(6):
+        g = gate(d["gates"][i].reshape(4, 3))
+        g.translate(d["t"][i] * d["velo"][i])                             # main.py:86-87
+        g.rotate_y(d["t"][i] * d["w"][i])
+        assert np.abs(g.transform(d["state"][i]) - d["inputs"][i, 0:13]).max() <= 1e-12
+        assert np.abs(g.t_final(d["final"][i]) - d["inputs"][i, 13:16]).max() <= 1e-12
+
+
+def test_closed_loop_episodes_match_tick_by_tick_oracle(oracle):
+    import torch
+    from learningagileflight_se3_b200 import quad_moving
+    from oracle import gate_oracle as G
+    O = oracle
+    d = np.load(GOLD)
+    dev = torch.device("cuda", 0)
+    B, ticks = 3, 2
+    rng = np.random.default_rng(11)
+    state0 = np.zeros((B, 13)); state0[:, 0:3] = rng.uniform(-2, 2, (B, 3)) + np.array([0, -6, 0]); state0[:, 6] = 1.0
+    final = rng.uniform(-1, 1, (B, 3)) + np.array([0, 6, 0])
+    gates = d["gates"][:B] * 1.0
+    gates = gates.reshape(B, 4, 3) - gates.reshape(B, 4, 3).mean(1, keepdims=True)     # gates around the origin
+    gates = gates.reshape(B, 12)
+    velo = np.tile(np.array([0.3, 0.1, 0.1]), (B, 1)); w = 0.5
+    net_t, net = _torch_net(d, dev), _np_net(d)
+    # DNN-2 stand-in with moderate outputs: traversal position/attitude small, time from the fixture network
+    def model_t(x):
+        y = net_t(x)
+        return torch.cat([0.1 * torch.tanh(y[:, 0:6]), y[:, 6:7]], 1)
+    def model_n(x):
+        y = net(x)
+        return np.concatenate([0.1 * np.tanh(y[0:6]), y[6:7]])
+    tt = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)  # noqa: E731
+    res = quad_moving.run_episodes(model_t, tt(state0), tt(final), tt(gates), tt(velo), w, n_ticks=ticks)
+    Ug = res["controls"].cpu().numpy()
+    p = O.default_params()
+    for b in range(B):
+        x, g, u = state0[b].copy(), gates[b].copy(), np.zeros(4)
+        for k in range(ticks):
+            t, _ = G.traversal_time(model_n, x, final[b], g, velo[b], w)
+            inp = G.gate_frame_inputs(g, velo[b], w, t, x, final[b])
+            out = model_n(inp)
+            pb = O.make_problem(inp[0:13], inp[13:16], out[0:3], O.rd2quat(out[3:6]), out[6], u)
+            sol = O.solve(p, pb)
+            u = sol["control_traj_opt"][0]
+            assert np.abs(Ug[b, k] - u).max() <= 1e-5, (b, k)            # north_star: controls within 1e-5
+            for _ in range(10):
+                x = G.plant_steps(x, u, 0.01, 1)
+                g = G.predict_gate(g, velo[b], w, 0.01)[0].reshape(12)
+        assert np.abs(res["state"][b].cpu().numpy() - x).max() <= 1e-6
