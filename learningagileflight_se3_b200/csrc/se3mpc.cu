@@ -6,8 +6,8 @@
 //                         atomic ticket so that the very different iteration counts of the NLPs do not leave a tail.
 //                         modes: solve (OCSys.ocSolver), objective (solve + reward fused in the epilogue),
 //                         sol_gradient (9 perturbed objectives per sample, quad_policy.py:94-112).
-//   se3mpc_reward_kernel  stand-alone rotor-tip roll-out + gate reward, one warp per trajectory, lanes <-> stages
-//                         (coalesced 13-double state loads): HBM-bound.
+//   se3mpc_reward_kernel  stand-alone rotor-tip roll-out + gate reward, one thread per trajectory, the states of 32 trajectories
+//                         streamed through shared memory with coalesced loads: HBM-bound.
 //   se3mpc_solgrad_epilogue  the clip/scale rule of sol_gradient over the 9 rewards of each sample.
 #include <cuda_runtime.h>
 
@@ -215,28 +215,70 @@ struct RArgs {
     int32_t *co;
 };
 
-__global__ void __launch_bounds__(256) se3mpc_reward_kernel(const __grid_constant__ RArgs a)
+// Stand-alone reward: one THREAD per trajectory, a warp streams its 32 trajectories through shared memory in chunks of RW_CH
+// stages: the global loads are coalesced (each trajectory's chunk is RW_CH*13 contiguous doubles, read 32 lanes wide), the
+// shared-memory rows have an odd stride so the per-thread reads are conflict-free.  HBM-bound: 5456 B per trajectory.
+#ifndef SE3_RW_CH
+#define SE3_RW_CH 3
+#endif
+#ifndef SE3_RW_CTAS
+#define SE3_RW_CTAS 4
+#endif
+constexpr int RW_CH = SE3_RW_CH, RW_ROW = RW_CH * 13, RW_STRIDE = RW_ROW | 1, RW_WARPS = 4, RW_CTAS = SE3_RW_CTAS;     // odd row stride
+
+__global__ void __launch_bounds__(RW_WARPS * 32, RW_CTAS) se3mpc_reward_kernel(const __grid_constant__ RArgs a)
 {
-    const int warps_per_cta = blockDim.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int N = a.par.N;
-    for (int pb = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); pb < a.B; pb += gridDim.x * warps_per_cta) {
-        const double *X = a.X + (size_t)pb * (N + 1) * 13;
+    __shared__ double stage_buf[RW_WARPS][32 * RW_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = a.par.N, nst = N + 1;
+    double *buf = stage_buf[warp];
+    const int ngroups = (a.B + 31) / 32;
+    for (int grp = blockIdx.x * RW_WARPS + warp; grp < ngroups; grp += gridDim.x * RW_WARPS) {
+        const int pb0 = grp * 32, pb = pb0 + lane;
+        const bool live = pb < a.B;
+        const int pbc = live ? pb : a.B - 1;
         double gate[12], goal[3];
-        for (int i = 0; i < 12; i++) gate[i] = __ldg(a.gate + (size_t)pb * 12 + i);
-        for (int i = 0; i < 3; i++) goal[i] = __ldg(a.goal + (size_t)pb * 3 + i);
-        double col, path;
-        int co;
-        const double r = se3::reward_warp(a.par, gate, goal,
-                                          [&](int s, double *x) {
 #pragma unroll
-                                              for (int i = 0; i < 13; i++) x[i] = __ldg(X + s * 13 + i);
-                                          },
-                                          &col, &path, &co);
-        if (lane == 0) {
+        for (int i = 0; i < 12; i++) gate[i] = __ldg(a.gate + (size_t)pbc * 12 + i);
+#pragma unroll
+        for (int i = 0; i < 3; i++) goal[i] = __ldg(a.goal + (size_t)pbc * 3 + i);
+        se3::RewardAcc acc;
+        acc.begin(a.par, gate);
+        const int nrows = min(32, a.B - pb0);
+        for (int s0 = 0; s0 < nst; s0 += RW_CH) {
+            const int cnt = min(RW_CH, nst - s0) * 13;                 // doubles per trajectory in this chunk
+            __syncwarp();
+            // coalesced: consecutive lanes read consecutive doubles of one trajectory's chunk
+            const double *src = a.X + ((size_t)pb0 * nst + s0) * 13;
+#pragma unroll 4
+            for (int j = 0; j < nrows; j++) {
+                const double *row = src + (size_t)j * nst * 13;
+#pragma unroll
+                for (int k0 = 0; k0 < RW_ROW; k0 += 32)
+                    if (k0 + lane < cnt) buf[j * RW_STRIDE + k0 + lane] = __ldg(row + k0 + lane);
+            }
+            __syncwarp();
+            if (live) {
+#pragma unroll 1
+                for (int q = 0; q * 13 < cnt; q++) {
+                    double x[13];
+#pragma unroll
+                    for (int i = 0; i < 13; i++) x[i] = buf[lane * RW_STRIDE + q * 13 + i];
+                    acc.consume(s0 + q, x, goal);
+                }
+            }
+        }
+        double col;
+        int co;
+        const double *Xp = a.X + (size_t)pbc * nst * 13;
+        const double r = acc.finish(gate, [&](int t, double *x) {
+#pragma unroll
+            for (int i = 0; i < 13; i++) x[i] = __ldg(Xp + t * 13 + i);
+        }, &col, &co);
+        if (live) {
             a.reward[pb] = r;
             if (a.collision) a.collision[pb] = col;
-            if (a.path) a.path[pb] = path;
+            if (a.path) a.path[pb] = acc.path;
             if (a.co) a.co[pb] = co;
         }
     }
@@ -471,11 +513,10 @@ int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const d
     if (B == 0) return SE3MPC_OK;
     RArgs a;
     a.par = *p; a.B = B; a.X = X; a.gate = gate; a.goal = goal; a.reward = reward; a.collision = collision; a.path = path; a.co = co;
-    const int warps_per_cta = 8;
-    int grid = (B + warps_per_cta - 1) / warps_per_cta;
-    const int cap = num_sms() * 8;
+    int grid = ((B + 31) / 32 + RW_WARPS - 1) / RW_WARPS;       // one thread per trajectory, RW_WARPS warps per CTA
+    const int cap = num_sms() * RW_CTAS * 2;
     if (grid > cap) grid = cap;
-    se3mpc_reward_kernel<<<grid, warps_per_cta * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    se3mpc_reward_kernel<<<grid, RW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return SE3MPC_OK;
