@@ -128,6 +128,16 @@ int se3mpc_sol_gradient_device(const se3mpc_params *p, int B, const double *x0, 
                                const double *tra_pos, const double *tra_ang, const double *t, const double *ulast,
                                double *out, int32_t *status9, void *workspace, size_t workspace_bytes, void *stream);
 
+/* se3mpc_solve_device started from a caller-supplied primal point (BASELINE.json configs[3]: receding-horizon re-solves warm
+ * started from the previous tick's shifted solution).  X_init[B][N+1][13] (row 0 ignored: x_0 is fixed by quad_OC.py:127-129),
+ * U_init[B][N][4]; either may be NULL (then that block keeps the reference's cold start of quad_OC.py:142,158).  The algorithm is
+ * unchanged -- it is IPOPT's treatment of any user x0: the point is pushed into the interior of the bounds (bound_push 1e-2),
+ * z = 1, least-squares multiplier estimate, mu_init from the parameters.  X_init / U_init must not alias X / U. */
+int se3mpc_solve_warm_device(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *tra_pos,
+                             const double *tra_att, int att_dim, const double *t, const double *ulast, int round_t,
+                             const double *X_init, const double *U_init, double *X, double *U, double *LAM, double *cost,
+                             const se3mpc_stats *stats, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- moving-gate closed loop (main.py:65-116), one thread per episode ----
  * se3mpc_gate_frame: gate(gate[b]).translate(t[b] velo[b]); .rotate_y(t[b] w[b])  (quad_model.py:686-700, 720-729), then the
  *   DNN-2 input packing of main.py:86-94 (same as quad_moving.py:35-42):

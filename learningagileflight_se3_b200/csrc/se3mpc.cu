@@ -38,6 +38,7 @@ struct KArgs {
     int nprob;                 // problems handed out (9*B in sol_gradient mode)
     int mode, round_t, att_dim;
     const double *x0, *goal, *gate, *tra_pos, *tra_ang, *t, *ulast;
+    const double *Xinit, *Uinit;      // optional primal starting points [nprob][N+1][13] / [nprob][N][4]
     double *X, *U, *LAM, *cost, *reward;
     int32_t *status, *iters, *nfact, *nls;
     double *kkt_error;
@@ -93,6 +94,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_
         else se3::rd2quat(ang, in.tra_q);
         in.t_tra = round_t ? se3::round1(t) : t;
         for (int j = 0; j < 4; j++) in.ulast[j] = with_ulast ? a.ulast[(size_t)src * 4 + j] : 0.0;
+        in.xinit = a.Xinit ? a.Xinit + (size_t)pb * (N + 1) * 13 : nullptr;
+        in.uinit = a.Uinit ? a.Uinit + (size_t)pb * N * 4 : nullptr;
 
         const se3::SolveStats st = se3::ipm_solve(c, a.par, in);
 
@@ -424,7 +427,8 @@ WsLayout layout(void *ws, int nproblems)
 int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, const double *x0, const double *goal,
                   const double *gate, const double *tra_pos, const double *tra_ang, int att_dim, const double *t, const double *ulast,
                   double *X, double *U, double *LAM, double *cost, double *reward, const se3mpc_stats *stats,
-                  int32_t *status_override, void *workspace, size_t workspace_bytes, cudaStream_t stream)
+                  int32_t *status_override, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                  const double *Xinit = nullptr, const double *Uinit = nullptr)
 {
     if (nprob <= 0) return SE3MPC_OK;
     WsLayout L = layout(workspace, nprob);
@@ -434,6 +438,7 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     a.par = *p; a.nprob = nprob; a.mode = mode; a.round_t = round_t; a.att_dim = att_dim;
     a.x0 = x0; a.goal = goal; a.gate = gate; a.tra_pos = tra_pos; a.tra_ang = tra_ang; a.t = t; a.ulast = ulast;
     a.X = X; a.U = U; a.LAM = LAM; a.cost = cost; a.reward = reward;
+    a.Xinit = Xinit; a.Uinit = Uinit;
     if (stats) { a.status = stats->status; a.iters = stats->iters; a.nfact = stats->nfact; a.nls = stats->nls; a.kkt_error = stats->kkt_error; }
     if (status_override) a.status = status_override;
     a.slots = L.slots; a.ticket = L.ticket;
@@ -503,6 +508,18 @@ int se3mpc_solve_device(const se3mpc_params *p, int B, const double *x0, const d
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     return launch_solver(p, MODE_SOLVE, B, round_t, x0, goal, nullptr, tra_pos, tra_ang, att_dim, t, ulast, X, U, LAM, cost, nullptr,
                          stats, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int se3mpc_solve_warm_device(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *tra_pos,
+                             const double *tra_ang, int att_dim, const double *t, const double *ulast, int round_t,
+                             const double *X_init, const double *U_init, double *X, double *U, double *LAM, double *cost,
+                             const se3mpc_stats *stats, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !x0 || !goal || !tra_pos || !tra_ang || !t || (att_dim != 3 && att_dim != 4) || (!X_init && !U_init))
+        return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    return launch_solver(p, MODE_SOLVE, B, round_t, x0, goal, nullptr, tra_pos, tra_ang, att_dim, t, ulast, X, U, LAM, cost, nullptr,
+                         stats, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), X_init, U_init);
 }
 
 int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const double *gate, const double *goal,

@@ -61,10 +61,11 @@ def _stats(B, device):
 
 
 def solve(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Optional[Params] = None,
-          want_traj=True, want_costate=True, want_state=True):
+          want_traj=True, want_costate=True, want_state=True, x_init=None, u_init=None):
     """OCSys.ocSolver for a batch (quad_OC.py:104-212).  Returns dict of device tensors.
 
-    tra_ang is [B,3] (the planner's Rodrigues-like vector, converted on the device) or [B,4] (traversal quaternion)."""
+    tra_ang is [B,3] (the planner's Rodrigues-like vector, converted on the device) or [B,4] (traversal quaternion).
+    x_init[B,N+1,13] / u_init[B,N,4]: optional primal starting point (se3mpc_solve_warm_device); default = the reference's cold start."""
     p = params or default_params()
     _require_cuda(x0, goal, tra_pos, tra_ang, t, ulast)
     B, N, dev = x0.reshape(-1, 13).shape[0], p.N, x0.device
@@ -76,11 +77,19 @@ def solve(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Opti
     LAM = torch.empty((B, N, 13), dtype=torch.float64, device=dev) if want_costate else None
     cost = torch.empty(B, dtype=torch.float64, device=dev)
     st, cs = _stats(B, dev)
+    _require_cuda(x_init, u_init)
+    x_init, u_init = _c(x_init, (B, N + 1, 13)), _c(u_init, (B, N, 4))
     with torch.cuda.device(dev):
         ws = _workspace(p, B, dev)
-        rc = _lib.lib().se3mpc_solve_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(tra_pos), _ptr(tra_ang), att_dim, _ptr(t), _ptr(ulast),
-                                            int(bool(round_t)), _ptr(X), _ptr(U), _ptr(LAM), _ptr(cost), C.byref(cs), _ptr(ws),
-                                            ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if x_init is None and u_init is None:
+            rc = _lib.lib().se3mpc_solve_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(tra_pos), _ptr(tra_ang), att_dim, _ptr(t), _ptr(ulast),
+                                                int(bool(round_t)), _ptr(X), _ptr(U), _ptr(LAM), _ptr(cost), C.byref(cs), _ptr(ws),
+                                                ws.numel(), stream)
+        else:
+            rc = _lib.lib().se3mpc_solve_warm_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(tra_pos), _ptr(tra_ang), att_dim, _ptr(t),
+                                                     _ptr(ulast), int(bool(round_t)), _ptr(x_init), _ptr(u_init), _ptr(X), _ptr(U), _ptr(LAM),
+                                                     _ptr(cost), C.byref(cs), _ptr(ws), ws.numel(), stream)
     _lib.check(rc, "se3mpc_solve_device")
     return {"state_traj_opt": X, "control_traj_opt": U, "costate_traj_opt": LAM, "cost": cost, **st}
 

@@ -63,10 +63,12 @@ def solver(model, quad_state, final_point, gate1, velo, w):
 
 @torch.no_grad()
 def run_episodes(model, state0, final_point, gate0, velo, w, n_ticks=50, sub_steps=10, dt_sim=0.01, params: Optional[Params] = None,
-                 gate_noise: Optional[torch.Tensor] = None, record=False):
+                 gate_noise: Optional[torch.Tensor] = None, record=False, warm_start=False):
     """Batched main.py:65-116.  state0[B,13], final_point[B,3], gate0[B,12] (corners at time 0), velo[B,3], w (scalar or [B]).
     The gate moves like gate.move (rotation about its y axis by w dt, translation by (velo + noise) dt per plant step); `gate_noise`
-    [n_ticks*sub_steps, B, 3] supplies the velocity noise (None: noise-free).  Returns the final states, the controls of every tick,
+    [n_ticks*sub_steps, B, 3] supplies the velocity noise (None: noise-free).  warm_start=False is the reference's behaviour (a fresh
+    run_quad per tick, cold start); warm_start=True starts every re-solve from the previous tick's solution shifted by one stage (one
+    MPC stage = one tick; BASELINE.json configs[3]).  Returns the final states, the controls of every tick,
     the per-tick solver status and traversal times (and the state trajectory at tick rate when record=True)."""
     p = params or default_params()
     dev = state0.device
@@ -76,16 +78,22 @@ def run_episodes(model, state0, final_point, gate0, velo, w, n_ticks=50, sub_ste
     w = torch.as_tensor(w, dtype=torch.float64, device=dev).expand(B).contiguous()
     u = torch.zeros(B, 4, dtype=torch.float64, device=dev)                                    # main.py:52
     zeros3 = torch.zeros(B, 3, dtype=torch.float64, device=dev)
-    U, ST, TT, XS = [], [], [], []
+    U, ST, TT, XS, IT = [], [], [], [], []
+    prev = None
     for k in range(n_ticks):
         vel_k = velo if gate_noise is None else velo + gate_noise[k * sub_steps]
         t, _ = traversal_time(model, state, final_point, gate, vel_k, w)                      # main.py:67
         inp = ops.gate_frame(gate, vel_k, w, t, state, final_point)                           # main.py:86-94
         out = model(inp).to(torch.float64)                                                    # main.py:96
+        xi = ui = None
+        if warm_start and prev is not None:                                                   # previous plan, one stage later
+            xi = torch.cat([prev["state_traj_opt"][:, 1:], prev["state_traj_opt"][:, -1:]], 1)
+            ui = torch.cat([prev["control_traj_opt"][:, 1:], prev["control_traj_opt"][:, -1:]], 1)
         sol = ops.solve(inp[:, 0:13], inp[:, 13:16], out[:, 0:3], out[:, 3:6], out[:, 6], ulast=u, round_t=False, params=p,
-                        want_costate=False, want_state=False)                                 # main.py:105-106 (get_input)
+                        want_costate=False, want_state=warm_start, x_init=xi, u_init=ui)      # main.py:105-106 (get_input)
+        prev = sol if warm_start else None
         u = sol["control_traj_opt"][:, 0, :].contiguous()
-        U.append(u); ST.append(sol["status"]); TT.append(t)
+        U.append(u); ST.append(sol["status"]); TT.append(t); IT.append(sol["iters"])
         if record:
             XS.append(state.clone())
         for j in range(sub_steps):                                                            # main.py:108 + gate.move
@@ -93,7 +101,8 @@ def run_episodes(model, state0, final_point, gate0, velo, w, n_ticks=50, sub_ste
             vel_j = velo if gate_noise is None else velo + gate_noise[k * sub_steps + j]
             # the gate as gate.move advances it: rotate about its centroid by w dt, then translate by vel dt = predicted gate at t = dt
             _, gate = ops.gate_frame(gate, vel_j, w, torch.full((B,), dt_sim, dtype=torch.float64, device=dev), state, final_point, want_gate=True)
-    res = {"state": state, "controls": torch.stack(U, 1), "status": torch.stack(ST, 1), "t_tra": torch.stack(TT, 1), "gate": gate}
+    res = {"state": state, "controls": torch.stack(U, 1), "status": torch.stack(ST, 1), "t_tra": torch.stack(TT, 1), "gate": gate,
+           "iters": torch.stack(IT, 1)}
     if record:
         res["states"] = torch.stack(XS, 1)
     return res

@@ -89,6 +89,8 @@ def lib():
         L.se3o_kkt_step.restype = C.c_int
         L.se3o_solve.argtypes = [C.POINTER(Params), C.POINTER(Problem), C.POINTER(Solution)]
         L.se3o_solve.restype = C.c_int
+        L.se3o_solve_from.argtypes = [C.POINTER(Params), C.POINTER(Problem), C.c_void_p, C.c_void_p, C.POINTER(Solution)]
+        L.se3o_solve_from.restype = C.c_int
         L.se3o_rotor_positions.argtypes = [C.POINTER(Params), dp, C.c_int, dp]
         L.se3o_collis_det.argtypes = [dp, dp, C.c_int, C.c_int, ip]
         L.se3o_collis_det.restype = C.c_double
@@ -231,9 +233,14 @@ def _sol_dict(p, sol: Solution):
     }
 
 
-def solve(p, pb):
+def solve(p, pb, x_init=None, u_init=None):
     sol = Solution()
-    lib().se3o_solve(C.byref(p), C.byref(pb), C.byref(sol))
+    if x_init is None and u_init is None:
+        lib().se3o_solve(C.byref(p), C.byref(pb), C.byref(sol))
+    else:
+        xi = None if x_init is None else _f64(x_init, (p.N + 1, 13))
+        ui = None if u_init is None else _f64(u_init, (p.N, 4))
+        lib().se3o_solve_from(C.byref(p), C.byref(pb), None if xi is None else xi.ctypes.data, None if ui is None else ui.ctypes.data, C.byref(sol))
     return _sol_dict(p, sol)
 
 

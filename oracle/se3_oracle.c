@@ -837,6 +837,13 @@ static int all_finite(const double *v, int n)
 
 int se3o_solve(const se3o_params *p, const se3o_problem *pb, se3o_solution *sol)
 {
+    return se3o_solve_from(p, pb, NULL, NULL, sol);
+}
+
+/* Same algorithm started from a user-supplied primal point (IPOPT's treatment of any x0: pushed into the interior of the
+ * bounds, z = 1, least-squares multipliers): the receding-horizon "warm start" of main.py-style closed loops. */
+int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *Xinit, const double *Uinit, se3o_solution *sol)
+{
     const int N = p->N;
     ipm_t *s = (ipm_t *)calloc(1, sizeof(ipm_t));
     s->p = p; s->pb = pb; s->N = N; s->sf = 1.0;
@@ -850,9 +857,12 @@ int se3o_solve(const se3o_params *p, const se3o_problem *pb, se3o_solution *sol)
     s->wU = p->w_bound + 1e-8 * fmax(1.0, fabs(p->w_bound));
     /* initial guess, quad_OC.py:128,142,158: x0 fixed, mid-point of bounds elsewhere (x_k = 0, u_k = (lb+ub)/2) */
     memcpy(s->x[0], pb->x0, sizeof(double) * NX);
-    for (int k = 1; k <= N; k++) memset(s->x[k], 0, sizeof(double) * NX);
+    for (int k = 1; k <= N; k++) {
+        if (Xinit) memcpy(s->x[k], Xinit + k * NX, sizeof(double) * NX);
+        else memset(s->x[k], 0, sizeof(double) * NX);
+    }
     for (int k = 0; k < N; k++)
-        for (int j = 0; j < NU; j++) s->u[k][j] = 0.5 * (p->u_lb + p->u_ub);
+        for (int j = 0; j < NU; j++) s->u[k][j] = Uinit ? Uinit[k * NU + j] : 0.5 * (p->u_lb + p->u_ub);
     /* push into the interior: bound_push = bound_frac = 1e-2 */
     {
         double pl = fmin(1e-2 * fmax(1.0, fabs(s->uL)), 1e-2 * (s->uU - s->uL));

@@ -33,12 +33,14 @@ gate0 = torch.as_tensor(sc["gate"], **f64)
 velo = torch.tensor([1.0, 0.3, 0.4], **f64).expand(B, 3).contiguous()          # main.py:45
 w = torch.pi / 2
 quad_moving.run_episodes(model, x0[:256], final[:256], gate0[:256], velo[:256], w, n_ticks=1)      # warm-up
-torch.cuda.synchronize()
-l0 = se3.launch_count()
-t0 = time.perf_counter()
-res = quad_moving.run_episodes(model, x0, final, gate0, velo, w, n_ticks=ticks)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-conv = int((res["status"] <= 1).sum())
-print(f"B {B} ticks {ticks}: {dt:.3f} s  -> {B * ticks / dt:.0f} closed-loop MPC solves/s ({conv}/{B * ticks} converged), "
-      f"{dt / ticks * 1e3:.1f} ms per tick, {se3.launch_count() - l0} kernel launches, mean traversal-time iterations n/a")
+for warm in (False, True):
+    torch.cuda.synchronize()
+    l0 = se3.launch_count()
+    t0 = time.perf_counter()
+    res = quad_moving.run_episodes(model, x0, final, gate0, velo, w, n_ticks=ticks, warm_start=warm)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    conv = int((res["status"] <= 1).sum())
+    print(f"B {B} ticks {ticks} {'warm' if warm else 'cold'} start: {dt:.3f} s -> {B * ticks / dt:.0f} closed-loop MPC solves/s ({conv}/{B * ticks} converged), "
+          f"{dt / ticks * 1e3:.1f} ms per tick, {se3.launch_count() - l0} kernel launches, mean IPM iterations per re-solve "
+          f"{res['iters'][:, 1:].double().mean().item():.1f}")

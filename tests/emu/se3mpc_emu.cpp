@@ -28,6 +28,7 @@ static void make_instance(const double *x0, const double *goal, const double *tr
     rd2quat(tra_ang, in.tra_q);
     in.t_tra = round_t ? round1(t) : t;
     for (int j = 0; j < 4; j++) in.ulast[j] = ulast ? ulast[j] : 0.0;
+    in.xinit = nullptr; in.uinit = nullptr;
 }
 
 extern "C" int se3emu_solve(const se3mpc_params *p, const double *x0, const double *goal, const double *tra_pos,

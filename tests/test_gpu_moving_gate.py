@@ -132,3 +132,56 @@ def test_closed_loop_episodes_match_tick_by_tick_oracle(oracle):
                 x = G.plant_steps(x, u, 0.01, 1)
                 g = G.predict_gate(g, velo[b], w, 0.01)[0].reshape(12)
         assert np.abs(res["state"][b].cpu().numpy() - x).max() <= 1e-6
+
+
+def test_warm_started_solve_matches_oracle_from_the_same_point(oracle):
+    """se3mpc_solve_warm_device vs the oracle started from the same primal point: a perturbed copy of the optimum (the receding-horizon
+    situation) -- same optimum, same tolerances as the cold start, fewer iterations."""
+    import torch
+    from learningagileflight_se3_b200 import ops
+    from tests.common import sample_scenarios
+    O = oracle
+    p = O.default_params()
+    B = 6
+    sc = sample_scenarios(B, 41)
+    dev = torch.device("cuda", 0)
+    tt = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)  # noqa: E731
+    cold = ops.solve(tt(sc["x0"]), tt(sc["goal"]), tt(sc["tra_pos"]), tt(sc["tra_ang"]), tt(sc["t"]), round_t=True)
+    rng = np.random.default_rng(2)
+    Xi = cold["state_traj_opt"].cpu().numpy() + rng.normal(0, 0.02, (B, 51, 13))
+    Ui = cold["control_traj_opt"].cpu().numpy() + rng.normal(0, 0.02, (B, 50, 4))
+    Ui[0, 3] = 5.0; Xi[1, 7, 10:13] = 9.0                                    # outside the bounds: must be pushed inside, not rejected
+    warm = ops.solve(tt(sc["x0"]), tt(sc["goal"]), tt(sc["tra_pos"]), tt(sc["tra_ang"]), tt(sc["t"]), round_t=True, x_init=tt(Xi), u_init=tt(Ui))
+    for i in range(B):
+        pb = O.make_problem(sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], O.rd2quat(sc["tra_ang"][i]), O.round1(sc["t"][i]))
+        so = O.solve(p, pb, x_init=Xi[i], u_init=Ui[i])
+        assert so["status"] == 0 and int(warm["status"][i]) == 0
+        assert abs(float(warm["cost"][i]) - so["cost"]) <= 1e-6 * abs(so["cost"])
+        assert np.abs(warm["state_traj_opt"][i].cpu().numpy() - so["state_traj_opt"]).max() <= 1e-5
+        assert np.abs(warm["control_traj_opt"][i].cpu().numpy() - so["control_traj_opt"]).max() <= 1e-5
+        assert abs(int(warm["iters"][i]) - so["iters"]) <= 3
+    assert float(warm["iters"].double().mean()) < float(cold["iters"].double().mean())
+
+
+def test_closed_loop_warm_start_reduces_iterations():
+    import torch
+    from learningagileflight_se3_b200 import quad_moving
+    from tests.common import sample_scenarios
+    d = np.load(GOLD)
+    dev = torch.device("cuda", 0)
+    B = 64
+    sc = sample_scenarios(B, 43)
+    net_t = _torch_net(d, dev)
+
+    def model(x):
+        y = net_t(x)
+        return torch.cat([0.1 * torch.tanh(y[:, 0:6]), y[:, 6:7]], 1)
+    tt = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)  # noqa: E731
+    velo = tt(np.tile(np.array([0.3, 0.1, 0.1]), (B, 1)))
+    cold = quad_moving.run_episodes(model, tt(sc["x0"]), tt(sc["goal"]), tt(sc["gate"]), velo, 0.5, n_ticks=4)
+    warm = quad_moving.run_episodes(model, tt(sc["x0"]), tt(sc["goal"]), tt(sc["gate"]), velo, 0.5, n_ticks=4, warm_start=True)
+    assert (warm["status"] <= 1).float().mean() >= 0.95 and (cold["status"] <= 1).float().mean() >= 0.95
+    assert torch.equal(cold["controls"][:, 0], warm["controls"][:, 0])                 # tick 0 is a cold start in both
+    ic, iw = cold["iters"][:, 1:].double().mean().item(), warm["iters"][:, 1:].double().mean().item()
+    print(f"closed loop mean IPM iterations per re-solve: cold {ic:.1f}, warm {iw:.1f}")
+    assert iw < ic
