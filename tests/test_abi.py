@@ -52,6 +52,10 @@ def test_compute_fails_loudly_without_a_device():
     with pytest.raises(Se3MpcError):
         ops.solve_host(np.zeros((1, 13)), np.zeros((1, 3)), np.zeros((1, 3)), np.zeros((1, 3)), np.ones(1))
     with pytest.raises(Se3MpcError):
+        ops.gate_frame_host(np.zeros((1, 12)), np.zeros((1, 3)), 0.0, 0.0, np.zeros((1, 13)), np.zeros((1, 3)))
+    with pytest.raises(Se3MpcError):
+        ops.plant_step_host(np.zeros((1, 13)), np.zeros((1, 4)))
+    with pytest.raises(Se3MpcError):
         ops.solve(torch.zeros(1, 13, dtype=torch.float64), torch.zeros(1, 3, dtype=torch.float64), torch.zeros(1, 3, dtype=torch.float64),
                   torch.zeros(1, 3, dtype=torch.float64), torch.ones(1, dtype=torch.float64))
 
