@@ -47,7 +47,10 @@ struct KArgs {
     const int32_t *order;      // longest-predicted-first processing order (or nullptr)
 };
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
+// Instantiated for 2 and for CTAS_PER_SM resident CTAs per SM: the launch bound sets the register budget (255 vs 168), and the
+// host picks the instance by batch size (ctas_per_sm_for).
+template <int CTAS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTA-shared per-lane work table (identical for every warp), then one WarpSmem per warp
@@ -384,9 +387,22 @@ int num_sms()
 
 constexpr size_t HDR_BYTES = 256;
 
+// Resident CTAs per SM for a launch of `nproblems`; the solver kernel is instantiated for 2 (255 registers) and for CTAS_PER_SM
+// (168 registers).  Fewer, fatter warps mean a lower per-problem latency (more registers, a larger share of the instruction
+// cache).  Measured on B200 (profiles/README.md): up to ~2 waves of problems the makespan is set by single-problem latency and
+// 2 CTAs/SM (8 warps) win by ~10%; for large batches 3 CTAs/SM (12 warps) give ~3% more throughput.
+// SE3MPC_CTAS_PER_SM overrides (tuning).
+int ctas_per_sm_for(int nproblems)
+{
+    static const int forced = [] { const char *e = getenv("SE3MPC_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (forced >= 1 && forced <= CTAS_PER_SM) return forced;
+    const int full = num_sms() * CTAS_PER_SM * WARPS_PER_CTA;
+    return (CTAS_PER_SM > 2 && nproblems <= 4 * full) ? 2 : CTAS_PER_SM;
+}
+
 int slots_for(int nproblems)
 {
-    const int cap = num_sms() * CTAS_PER_SM * WARPS_PER_CTA;
+    const int cap = num_sms() * ctas_per_sm_for(nproblems) * WARPS_PER_CTA;
     int s = nproblems < cap ? nproblems : cap;
     s = (s + WARPS_PER_CTA - 1) / WARPS_PER_CTA * WARPS_PER_CTA;
     return s < WARPS_PER_CTA ? WARPS_PER_CTA : s;
@@ -456,9 +472,13 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     }
     const size_t smem = se3::LTAB_BYTES + sizeof(se3::WarpSmem) * WARPS_PER_CTA;
     static std::once_flag once;
-    std::call_once(once, [&] { cudaFuncSetAttribute(se3mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    std::call_once(once, [&] {
+        cudaFuncSetAttribute(se3mpc_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
     const int grid = L.nslots / WARPS_PER_CTA;
-    se3mpc_solve_kernel<<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    if (ctas_per_sm_for(nprob) <= 2) se3mpc_solve_kernel<2><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    else se3mpc_solve_kernel<CTAS_PER_SM><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return SE3MPC_OK;
