@@ -10,7 +10,13 @@ src_csv = sys.argv[1]
 lib = sys.argv[2] if len(sys.argv) > 2 else "learningagileflight_se3_b200/csrc/libse3mpc.so"
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 funcs = [(0, "solve_kernel body (ipm loop, reward, init)")]
+# the solver kernel is instantiated twice (se3mpc_solve_kernel<2>, <3>): pick the instance the capture is of
+first = open(src_csv).readline()
+inst = re.search(r"solve_kernel<(?:\(int\))?(\d)>", first)
+tag = f"solve_kernelILi{inst.group(1)}E" if inst else "solve_kernel"
 for line in elf.split("\n"):
+    if tag not in line:
+        continue
     m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+\S+\s+\S+\s+\S+\s+\$\S*solve_kernel[A-Za-z0-9_]*\$(\S+)", line)
     if m:
         name = m.group(3)
