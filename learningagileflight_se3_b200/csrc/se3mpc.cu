@@ -2,13 +2,15 @@
 // se3mpc_core.cuh for the warp-cooperative interior-point solver.
 //
 // Kernels
-//   se3mpc_solve_kernel   persistent warps (8 per SM, 255 registers each), one problem per warp at a time, problems handed out by an
-//                         atomic ticket so that the very different iteration counts of the NLPs do not leave a tail.
+//   se3mpc_solve_kernel<CTAS>  persistent warps, one problem per warp at a time, problems handed out by an atomic ticket in
+//                         longest-predicted-first order so that the very different iteration counts of the NLPs leave a short tail.
+//                         Two instances: 8 warps/SM x 255 registers (small launches: latency) and 12 warps/SM x 168 registers.
 //                         modes: solve (OCSys.ocSolver), objective (solve + reward fused in the epilogue),
 //                         sol_gradient (9 perturbed objectives per sample, quad_policy.py:94-112).
 //   se3mpc_reward_kernel  stand-alone rotor-tip roll-out + gate reward, one thread per trajectory, the states of 32 trajectories
 //                         streamed through shared memory with coalesced loads: HBM-bound.
 //   se3mpc_solgrad_epilogue  the clip/scale rule of sol_gradient over the 9 rewards of each sample.
+//   se3mpc_gate_frame_kernel, se3mpc_plant_step_kernel  the per-tick pieces of the moving-gate closed loop (main.py:65-116).
 #include <cuda_runtime.h>
 
 #include <atomic>
