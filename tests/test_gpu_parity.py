@@ -203,3 +203,37 @@ def test_torch_custom_op_and_full_batch_properties(se3, oracle):
     assert same.sum() >= 23
     assert np.all(np.abs(cg - ro["cost"])[same] <= 1e-6 * np.abs(ro["cost"])[same])
     assert np.all(np.abs(rg - ro["reward"])[same] <= 1e-6 * np.maximum(1, np.abs(ro["reward"]))[same])
+
+
+def test_edge_cases_empty_ragged_horizons_and_bad_arguments(oracle, se3):
+    """Empty and ragged batches (1, 3, 5, 33 problems: below / across the 4-warp CTA granularity), the shortest and the longest
+    supported horizon, order independence, and argument errors (codes, no crash, no CPU fallback)."""
+    from learningagileflight_se3_b200 import Se3MpcError
+    p = oracle.default_params()
+    sc = sample_scenarios(33, 301)
+    keys = ("x0", "goal", "tra_pos", "tra_ang", "t")
+    full = se3.ops.solve_host(*(sc[k] for k in keys), round_t=True)
+    assert (full["status"] == 0).all()
+    for B in (0, 1, 3, 5):
+        r = se3.ops.solve_host(*(sc[k][:B] for k in keys), round_t=True)
+        assert r["state_traj_opt"].shape == (B, 51, 13) and r["control_traj_opt"].shape == (B, 50, 4) and r["cost"].shape == (B,)
+        assert np.array_equal(r["state_traj_opt"], full["state_traj_opt"][:B]) and np.array_equal(r["cost"], full["cost"][:B])
+    perm = np.random.default_rng(0).permutation(33)                      # results do not depend on the position in the batch
+    rp = se3.ops.solve_host(*(sc[k][perm] for k in keys), round_t=True)
+    assert np.array_equal(rp["control_traj_opt"], full["control_traj_opt"][perm])
+    for N in (2, 63):                                                     # SE3MPC_MAX_HORIZON = 63 (64 stage columns per row)
+        pn = se3.default_params(N=N)
+        po = oracle.default_params(N=N)
+        r = se3.ops.solve_host(*(sc[k][:2] for k in keys), round_t=True, params=pn)
+        for i in range(2):
+            pb = oracle.make_problem(sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], oracle.rd2quat(sc["tra_ang"][i]), oracle.round1(sc["t"][i]))
+            so = oracle.solve(po, pb)
+            assert so["status"] == int(r["status"][i]) == 0
+            assert abs(r["cost"][i] - so["cost"]) <= 1e-6 * abs(so["cost"])
+            assert np.abs(r["state_traj_opt"][i] - so["state_traj_opt"]).max() <= 1e-5
+    with pytest.raises(Se3MpcError):
+        se3.ops.solve_host(*(sc[k][:1] for k in keys), params=se3.default_params(N=64))          # horizon too long
+    with pytest.raises(Se3MpcError):
+        se3.ops.solve_host(*(sc[k][:1] for k in keys), params=se3.default_params(att_power=3))   # unknown cost variant
+    with pytest.raises(Se3MpcError):
+        se3.ops.solve(torch.zeros(1, 13, dtype=torch.float32, device="cuda"), _t(sc["goal"][:1]), _t(sc["tra_pos"][:1]), _t(sc["tra_ang"][:1]), _t(sc["t"][:1]))
