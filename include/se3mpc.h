@@ -149,6 +149,10 @@ int se3mpc_gate_frame_device(int B, const double *gate, const double *velo, cons
                              const double *state, const double *final_point, double *inputs18, double *gate_pred, void *stream);
 int se3mpc_plant_step_device(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state, void *stream);
 
+/* Quadrotor.get_quadrotor_position (quad_model.py:239-276): X[nstates][13] -> pos[nstates][15] = centre of mass + the four rotor
+ * tips r + R(q)^T b_i, b_i = (+-a, +-a, 0), a = wing_len * 0.5 / sqrt(2), with the reference's un-normalised quaternion. */
+int se3mpc_rotor_positions_device(int nstates, double wing_len, const double *X, double *pos, void *stream);
+
 /* Host-buffer variants: same semantics, HOST pointers, synchronous (H2D + kernels + D2H inside). */
 int se3mpc_solve_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *tra_pos,
                       const double *tra_att, int att_dim, const double *t, const double *ulast, int round_t,
@@ -159,6 +163,7 @@ int se3mpc_collis_det_host(int B, int horizon, const double *V, const double *ga
 int se3mpc_gate_frame_host(int B, const double *gate, const double *velo, const double *w, const double *t, const double *state,
                            const double *final_point, double *inputs18, double *gate_pred);
 int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state);
+int se3mpc_rotor_positions_host(int nstates, double wing_len, const double *X, double *pos);
 int se3mpc_objective_host(const se3mpc_params *p, int B, const double *x0, const double *goal, const double *gate,
                           const double *tra_pos, const double *tra_ang, const double *t, const double *ulast,
                           double *reward, double *X, double *U, double *cost, const se3mpc_stats *stats);

@@ -48,7 +48,7 @@ EXPORTS = [
     "se3mpc_solve_device", "se3mpc_reward_device", "se3mpc_collis_det_device", "se3mpc_objective_device",
     "se3mpc_sol_gradient_device", "se3mpc_solve_host", "se3mpc_reward_host", "se3mpc_collis_det_host",
     "se3mpc_objective_host", "se3mpc_sol_gradient_host", "se3mpc_host_release", "se3mpc_launch_count", "se3mpc_fp64_probe_device",
-    "se3mpc_gate_frame_device", "se3mpc_gate_frame_host", "se3mpc_plant_step_device", "se3mpc_plant_step_host", "se3mpc_solve_warm_device",
+    "se3mpc_gate_frame_device", "se3mpc_gate_frame_host", "se3mpc_plant_step_device", "se3mpc_plant_step_host", "se3mpc_solve_warm_device", "se3mpc_rotor_positions_device", "se3mpc_rotor_positions_host",
 ]
 
 
@@ -85,6 +85,9 @@ def lib():
     L.se3mpc_solve_device.argtypes = [pp, ci, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp, sp, vp, C.c_size_t, vp]
     L.se3mpc_solve_warm_device.argtypes = [pp, ci, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp, vp, vp, sp, vp, C.c_size_t, vp]
     L.se3mpc_solve_warm_device.restype = ci
+    L.se3mpc_rotor_positions_device.argtypes = [ci, C.c_double, vp, vp, vp]
+    L.se3mpc_rotor_positions_host.argtypes = [ci, C.c_double, vp, vp]
+    L.se3mpc_rotor_positions_device.restype = L.se3mpc_rotor_positions_host.restype = ci
     L.se3mpc_reward_device.argtypes = [pp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
     L.se3mpc_fp64_probe_device.argtypes = [ci, vp, vp, C.POINTER(C.c_double)]
     L.se3mpc_fp64_probe_device.restype = ci

@@ -215,6 +215,22 @@ __global__ void se3mpc_plant_step_kernel(const __grid_constant__ se3mpc_params p
     for (int i = 0; i < 13; i++) state[(size_t)b * 13 + i] = x[i];
 }
 
+// quad_model.py:239-276 get_quadrotor_position: centre of mass + the four rotor tips of every state, one thread per state
+__global__ void se3mpc_rotor_positions_kernel(int nstates, double arm, const double *X, double *pos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nstates) return;
+    double x[13];
+    for (int k = 0; k < 13; k++) x[k] = X[(size_t)i * 13 + k];
+    double *o = pos + (size_t)i * 15;
+    o[0] = x[0]; o[1] = x[1]; o[2] = x[2];
+    for (int r = 0; r < 4; r++) {
+        double tip[3];
+        se3::rotor_tip(x, r, arm, tip);
+        o[3 + 3 * r] = tip[0]; o[4 + 3 * r] = tip[1]; o[5 + 3 * r] = tip[2];
+    }
+}
+
 struct RArgs {
     se3mpc_params par;
     int B;
@@ -831,6 +847,37 @@ int se3mpc_plant_step_device(const se3mpc_params *p, int B, double dt, int nstep
     se3mpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, B, dt, nsteps, u, state);
     g_launches++;
     CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_rotor_positions_device(int nstates, double wing_len, const double *X, double *pos, void *stream)
+{
+    if (nstates < 0 || !X || !pos) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (nstates == 0) return SE3MPC_OK;
+    se3mpc_rotor_positions_kernel<<<(nstates + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(nstates, wing_len * 0.5 / sqrt(2.0), X, pos);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_rotor_positions_host(int nstates, double wing_len, const double *X, double *pos)
+{
+    if (nstates < 0 || !X || !pos) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (nstates == 0) return SE3MPC_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = g_in.ensure(pad((size_t)nstates * 13 * 8))) != SE3MPC_OK) return rc;
+    if ((rc = g_out.ensure(pad((size_t)nstates * 15 * 8))) != SE3MPC_OK) return rc;
+    double *d_x = static_cast<double *>(g_in.p), *d_p = static_cast<double *>(g_out.p);
+    cudaStream_t s = g_stream;
+    CK(cudaMemcpyAsync(d_x, X, (size_t)nstates * 13 * 8, cudaMemcpyHostToDevice, s));
+    rc = se3mpc_rotor_positions_device(nstates, wing_len, d_x, d_p, s);
+    if (rc != SE3MPC_OK) return rc;
+    CK(cudaMemcpyAsync(pos, d_p, (size_t)nstates * 15 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return SE3MPC_OK;
 }
 

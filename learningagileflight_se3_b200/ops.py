@@ -310,6 +310,15 @@ def plant_step_host(state, u, dt=0.01, nsteps=1, params: Optional[Params] = None
     return x
 
 
+def rotor_positions_host(X, wing_len):
+    """Quadrotor.get_quadrotor_position (quad_model.py:239-276) for any number of states: X[...,13] -> pos[...,15] (numpy)."""
+    X = _np(X, (-1, 13))
+    pos = np.empty((X.shape[0], 15))
+    rc = _lib.lib().se3mpc_rotor_positions_host(X.shape[0], float(wing_len), _np_ptr(X), _np_ptr(pos))
+    _lib.check(rc, "se3mpc_rotor_positions_host")
+    return pos
+
+
 # ---- torch custom ops: torch.ops.se3mpc.{solve,reward,objective,sol_gradient} (CUDA dispatch key only) ------
 _registered = False
 

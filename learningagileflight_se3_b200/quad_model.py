@@ -84,45 +84,18 @@ class Quadrotor:
         self.dt_plant = float(dt)
 
     def dyn_fn(self, state, control):
-        """x + dt*f(x,u) on the host (closed-loop plant of main.py:108); numpy, single state."""
+        """x + dt*f(x,u) (closed-loop plant of main.py:108) through se3mpc_plant_step (one Euler step on the GPU)."""
         if self.dt_plant is None:
             raise RuntimeError("call setDyn(dt) first")
-        x = np.asarray(state, dtype=float).reshape(13)
-        u = np.asarray(control, dtype=float).reshape(4)
-        q0, q1, q2, q3 = x[6:10]
-        wx, wy, wz = x[10:13]
-        T = u.sum()
-        f = np.empty(13)
-        f[0:3] = x[3:6]
-        f[3] = T / self.mass * 2 * (q1 * q3 + q0 * q2)
-        f[4] = T / self.mass * 2 * (q2 * q3 - q0 * q1)
-        f[5] = T / self.mass * (1 - 2 * (q1 * q1 + q2 * q2)) - self.g
-        f[6] = 0.5 * (-wx * q1 - wy * q2 - wz * q3)
-        f[7] = 0.5 * (wx * q0 + wz * q2 - wy * q3)
-        f[8] = 0.5 * (wy * q0 - wz * q1 + wx * q3)
-        f[9] = 0.5 * (wz * q0 + wy * q1 - wx * q2)
-        Mx, My = (u[3] - u[1]) * self.l / 2, (u[2] - u[0]) * self.l / 2
-        Mz = (u[0] - u[1] + u[2] - u[3]) * self.c
-        f[10] = (Mx - (self.Jz - self.Jy) * wy * wz) / self.Jx
-        f[11] = (My - (self.Jx - self.Jz) * wx * wz) / self.Jy
-        f[12] = (Mz - (self.Jy - self.Jx) * wx * wy) / self.Jz
-        return x + self.dt_plant * f
+        from . import ops
+        p = ops.default_params(Jx=self.Jx, Jy=self.Jy, Jz=self.Jz, mass=self.mass, arm_l=self.l, c_tau=self.c, grav=self.g)
+        return ops.plant_step_host(np.asarray(state, dtype=float).reshape(1, 13), np.asarray(control, dtype=float).reshape(1, 4),
+                                   self.dt_plant, 1, params=p)[0]
 
-    # quad_model.py:239-276 (host version, used by the shim for `self.traj`; the kernels have their own)
+    # quad_model.py:239-276
     def get_quadrotor_position(self, wing_len, state_traj):
-        X = np.asarray(state_traj, dtype=float).reshape(-1, 13)
-        a = wing_len * 0.5 / math.sqrt(2.0)
-        body = np.array([[a, a, 0.0], [-a, a, 0.0], [-a, -a, 0.0], [a, -a, 0.0]])
-        q0, q1, q2, q3 = X[:, 6], X[:, 7], X[:, 8], X[:, 9]
-        C = np.empty((X.shape[0], 3, 3))         # world->body direction cosine matrix, no normalisation
-        C[:, 0, 0] = 1 - 2 * (q2 * q2 + q3 * q3); C[:, 0, 1] = 2 * (q1 * q2 + q0 * q3); C[:, 0, 2] = 2 * (q1 * q3 - q0 * q2)
-        C[:, 1, 0] = 2 * (q1 * q2 - q0 * q3); C[:, 1, 1] = 1 - 2 * (q1 * q1 + q3 * q3); C[:, 1, 2] = 2 * (q2 * q3 + q0 * q1)
-        C[:, 2, 0] = 2 * (q1 * q3 + q0 * q2); C[:, 2, 1] = 2 * (q2 * q3 - q0 * q1); C[:, 2, 2] = 1 - 2 * (q1 * q1 + q2 * q2)
-        pos = np.empty((X.shape[0], 15))
-        pos[:, 0:3] = X[:, 0:3]
-        for r in range(4):
-            pos[:, 3 * (r + 1):3 * (r + 2)] = X[:, 0:3] + np.einsum("tji,j->ti", C, body[r])
-        return pos
+        from . import ops
+        return ops.rotor_positions_host(np.asarray(state_traj, dtype=float).reshape(-1, 13), wing_len)
 
 
 class gate:

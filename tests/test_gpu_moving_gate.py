@@ -185,3 +185,20 @@ def test_closed_loop_warm_start_reduces_iterations():
     ic, iw = cold["iters"][:, 1:].double().mean().item(), warm["iters"][:, 1:].double().mean().item()
     print(f"closed loop mean IPM iterations per re-solve: cold {ic:.1f}, warm {iw:.1f}")
     assert iw < ic
+
+
+def test_quadrotor_shim_plant_and_rotor_positions_run_on_the_gpu(oracle):
+    """Quadrotor.dyn_fn (main.py:108) and get_quadrotor_position (quad_model.py:239-276) of the mirror class go through the C ABI."""
+    from learningagileflight_se3_b200 import ops
+    from learningagileflight_se3_b200.quad_model import Quadrotor
+    from oracle import gate_oracle as G
+    rng = np.random.default_rng(8)
+    uav = Quadrotor()
+    uav.initDyn(Jx=0.0023, Jy=0.0023, Jz=0.004, mass=0.5, l=0.35, c=0.0245)
+    uav.setDyn(0.01)
+    x, u = rng.normal(0, 1, 13), rng.uniform(0, 2.4, 4)
+    assert np.abs(uav.dyn_fn(x, u) - G.plant_steps(x, u, 0.01, 1)).max() <= 1e-13
+    X = rng.normal(0, 1, (51, 13))
+    p = oracle.default_params()
+    assert np.abs(uav.get_quadrotor_position(1.5, X) - oracle.rotor_positions(p, X)).max() <= 1e-13
+    assert ops.rotor_positions_host(np.zeros((0, 13)), 1.5).shape == (0, 15)
