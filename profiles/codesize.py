@@ -15,6 +15,9 @@ for line in elf.split("\n"):
         if mm: name = name[len(mm.group(0)):len(mm.group(0)) + int(mm.group(1))]
         seen[name] = int(m.group(2), 16)
 tot = seen.pop("(whole kernel)", 0)
+if not tot:      # the kernel's own symbol has no '$': take the size of its .text section
+    m = re.search(r"\s([0-9a-f]+)\s+0\s+80\s+PROGBITS\s+\S+\s+\S+\s+\S+\s+\.text\.\S*" + tag, elf)
+    tot = int(m.group(1), 16) if m else 0
 for k, v in sorted(seen.items(), key=lambda kv: -kv[1]): print(f"{v:8d} B  {k}")
 print(f"{tot - sum(seen.values()):8d} B  kernel body (inlined ipm_solve, reward, init)")
 print(f"{tot:8d} B  se3mpc_solve_kernel<{inst}> total")
