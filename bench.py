@@ -44,7 +44,7 @@ W_SOLVE = N_H * 1124.0
 W_EVAL = N_H * 600.0
 W_LS = N_H * 150.0
 # DRAM bytes per problem of se3mpc_solve_kernel from the committed ncu capture (profiles/README.md): slot traffic (records, factors)
-NCU_DRAM_BYTES_PER_PROBLEM = 33.6e6
+NCU_DRAM_BYTES_PER_PROBLEM = 29.7e6
 
 
 def algorithmic_flops(iters, nfact, nls):
