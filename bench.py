@@ -45,6 +45,7 @@ W_EVAL = N_H * 600.0
 W_LS = N_H * 150.0
 # DRAM bytes per problem of se3mpc_solve_kernel from the committed ncu capture (profiles/README.md): slot traffic (records, factors)
 NCU_DRAM_BYTES_PER_PROBLEM = 29.7e6
+NCU_REWARD_DRAM_BYTES_PER_TRAJECTORY = 6495.0     # se3mpc_reward_kernel, same source (5456 algorithmic)
 
 
 def algorithmic_flops(iters, nfact, nls):
@@ -276,7 +277,8 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ach_r = rb / (min(tr) * 1e-3) / 1e9
         roofline_reward = {"bound": "hbm", "kernel": "se3mpc_reward_kernel", "achieved": ach_r, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": ach_r / hbm_peak, "traffic": None, "trajectories": NB,
+                           "frac": ach_r / hbm_peak, "traffic": NCU_REWARD_DRAM_BYTES_PER_TRAJECTORY * NB, "trajectories": NB,
+                           "traffic_source": "ncu --set full of one 2^18-trajectory launch (profiles/r1_ncu_full_raw_reward_kernel.csv): 16-byte-granular bulk copies of 8-byte-aligned 416 B chunks over-fetch ~18%",
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
         del Xr
         cpu_b = None

@@ -8,7 +8,7 @@
 //                         modes: solve (OCSys.ocSolver), objective (solve + reward fused in the epilogue),
 //                         sol_gradient (9 perturbed objectives per sample, quad_policy.py:94-112).
 //   se3mpc_reward_kernel  stand-alone rotor-tip roll-out + gate reward, one thread per trajectory, the states of 32 trajectories
-//                         streamed through shared memory with coalesced loads: HBM-bound.
+//                         streamed through shared memory by per-lane TMA bulk copies (double-buffered): HBM-bound.
 //   se3mpc_solgrad_epilogue  the clip/scale rule of sol_gradient over the 9 rewards of each sample.
 //   se3mpc_gate_frame_kernel, se3mpc_plant_step_kernel  the per-tick pieces of the moving-gate closed loop (main.py:65-116).
 #include <cuda_runtime.h>
@@ -239,28 +239,70 @@ struct RArgs {
     int32_t *co;
 };
 
-// Stand-alone reward: one THREAD per trajectory, a warp streams its 32 trajectories through shared memory in chunks of RW_CH
-// stages: the global loads are coalesced (each trajectory's chunk is RW_CH*13 contiguous doubles, read 32 lanes wide), the
-// shared-memory rows have an odd stride so the per-thread reads are conflict-free.  HBM-bound: 5456 B per trajectory.
+// Stand-alone reward: one THREAD per trajectory; a warp streams its 32 trajectories through shared memory in chunks of RW_CH
+// stages.  The chunk of a trajectory is RW_CH*13 contiguous doubles in HBM: each lane fetches its own chunk with ONE bulk
+// asynchronous copy (cp.async.bulk, the TMA engine; completion on a per-warp mbarrier) into one of two buffers while the
+// threads consume the other, so the copy costs one instruction per chunk and 6.5 KB per warp are always in flight.
+// Trajectories are only 8-byte aligned (5304 B each), bulk copies need 16: a copy starts at the aligned-down address and
+// the consumer skips the leading double.  Rows have an odd stride (conflict-free per-thread LDS.64).  HBM-bound: 5456 B per
+// trajectory.
 #ifndef SE3_RW_CH
-#define SE3_RW_CH 3
+#define SE3_RW_CH 4
 #endif
 #ifndef SE3_RW_CTAS
-#define SE3_RW_CTAS 4
+#define SE3_RW_CTAS 2
 #endif
-constexpr int RW_CH = SE3_RW_CH, RW_ROW = RW_CH * 13, RW_STRIDE = RW_ROW | 1, RW_WARPS = 4, RW_CTAS = SE3_RW_CTAS;     // odd row stride
+#ifndef SE3_RW_NBUF
+#define SE3_RW_NBUF 2
+#endif
+constexpr int RW_CH = SE3_RW_CH, RW_ROW = RW_CH * 13, RW_STRIDE = (RW_ROW + 3) | 1, RW_WARPS = 4, RW_CTAS = SE3_RW_CTAS;
+constexpr int RW_NBUF = SE3_RW_NBUF;                  // buffers (chunks in flight + 1) per warp
+constexpr size_t RW_BUF = (size_t)RW_WARPS * RW_NBUF * 32 * RW_STRIDE * sizeof(double);
+constexpr size_t RW_SMEM = RW_BUF + RW_WARPS * RW_NBUF * sizeof(unsigned long long);
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(RW_WARPS * 32, RW_CTAS) se3mpc_reward_kernel(const __grid_constant__ RArgs a)
 {
-    __shared__ double stage_buf[RW_WARPS][32 * RW_STRIDE];
+    extern __shared__ __align__(16) double rw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = a.par.N, nst = N + 1;
-    double *buf = stage_buf[warp];
+    const int N = a.par.N, nst = N + 1, nch = (nst + RW_CH - 1) / RW_CH;
+    double *buf = rw_smem + (size_t)warp * RW_NBUF * 32 * RW_STRIDE;
+    const unsigned bar0 = smem_u32(reinterpret_cast<unsigned char *>(rw_smem) + RW_BUF) + warp * RW_NBUF * 8;     // one mbarrier per buffer
+    if (lane == 0) {
+        for (int b = 0; b < RW_NBUF; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(bar0 + b * 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const size_t total = (size_t)a.B * nst * 13;          // doubles in X
+    const int row0 = lane * RW_STRIDE + ((lane * RW_STRIDE) & 1);      // 16-byte aligned start of this lane's row
+    unsigned gch = 0;                                     // chunks consumed so far: buffer = gch % NBUF, phase parity = (gch / NBUF) & 1
     const int ngroups = (a.B + 31) / 32;
     for (int grp = blockIdx.x * RW_WARPS + warp; grp < ngroups; grp += gridDim.x * RW_WARPS) {
         const int pb0 = grp * 32, pb = pb0 + lane;
         const bool live = pb < a.B;
         const int pbc = live ? pb : a.B - 1;
+        const size_t base = (size_t)pbc * nst * 13;
+        // chunk ch of this lane's trajectory -> its row of buffer g & 1; returns the offset of the first state in the row
+        auto issue = [&](const int ch, const unsigned g) {
+            const unsigned bar = bar0 + (g % RW_NBUF) * 8;
+            if (live) {
+                const int s0 = ch * RW_CH, cnt = min(RW_CH, nst - s0) * 13;
+                const size_t off = base + (size_t)s0 * 13;
+                const int shift = (int)((reinterpret_cast<size_t>(a.X + off) >> 3) & 1);
+                int n = (cnt + shift + 1) & ~1;
+                if (off - shift + n > total) n -= 2;                        // never read past the end of X (tail fixed up by the consumer)
+                const unsigned dst = smem_u32(buf + (g % RW_NBUF) * 32 * RW_STRIDE + row0);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n * 8) : "memory");
+                if (n > 0)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(a.X + off - shift), "r"(n * 8), "r"(bar) : "memory");
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            }
+        };
+        __syncwarp();
+        for (int d = 0; d < RW_NBUF - 1 && d < nch; d++) issue(d, gch + d);
         double gate[12], goal[3];
 #pragma unroll
         for (int i = 0; i < 12; i++) gate[i] = __ldg(a.gate + (size_t)pbc * 12 + i);
@@ -268,29 +310,32 @@ __global__ void __launch_bounds__(RW_WARPS * 32, RW_CTAS) se3mpc_reward_kernel(c
         for (int i = 0; i < 3; i++) goal[i] = __ldg(a.goal + (size_t)pbc * 3 + i);
         se3::RewardAcc acc;
         acc.begin(a.par, gate);
-        const int nrows = min(32, a.B - pb0);
-        for (int s0 = 0; s0 < nst; s0 += RW_CH) {
-            const int cnt = min(RW_CH, nst - s0) * 13;                 // doubles per trajectory in this chunk
-            __syncwarp();
-            // coalesced: consecutive lanes read consecutive doubles of one trajectory's chunk
-            const double *src = a.X + ((size_t)pb0 * nst + s0) * 13;
-#pragma unroll 4
-            for (int j = 0; j < nrows; j++) {
-                const double *row = src + (size_t)j * nst * 13;
-#pragma unroll
-                for (int k0 = 0; k0 < RW_ROW; k0 += 32)
-                    if (k0 + lane < cnt) buf[j * RW_STRIDE + k0 + lane] = __ldg(row + k0 + lane);
+        for (int ch = 0; ch < nch; ch++, gch++) {
+            if (ch + RW_NBUF - 1 < nch) issue(ch + RW_NBUF - 1, gch + RW_NBUF - 1);
+            {
+                const unsigned bar = bar0 + (gch % RW_NBUF) * 8, parity = (gch / RW_NBUF) & 1;
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
             }
-            __syncwarp();
+            const int s0 = ch * RW_CH, cnt = min(RW_CH, nst - s0) * 13;
             if (live) {
+                const size_t off = base + (size_t)s0 * 13;
+                const int shift = (int)((reinterpret_cast<size_t>(a.X + off) >> 3) & 1);
+                double *cur = buf + (gch % RW_NBUF) * 32 * RW_STRIDE + row0 + shift;
+                const int n = (cnt + shift + 1) & ~1;
+                if (off - shift + n > total)                                 // the copy stopped 16 bytes early: last double(s) by hand
+                    for (int i = n - 2 - shift; i < cnt; i++) cur[i] = __ldg(a.X + off + i);
 #pragma unroll 1
                 for (int q = 0; q * 13 < cnt; q++) {
                     double x[13];
 #pragma unroll
-                    for (int i = 0; i < 13; i++) x[i] = buf[lane * RW_STRIDE + q * 13 + i];
+                    for (int i = 0; i < 13; i++) x[i] = cur[q * 13 + i];
                     acc.consume(s0 + q, x, goal);
                 }
             }
+            __syncwarp();           // every lane is done with this buffer before the issue of the next iteration refills it
         }
         double col;
         int co;
@@ -571,7 +616,9 @@ int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const d
     int grid = ((B + 31) / 32 + RW_WARPS - 1) / RW_WARPS;       // one thread per trajectory, RW_WARPS warps per CTA
     const int cap = num_sms() * RW_CTAS * 2;
     if (grid > cap) grid = cap;
-    se3mpc_reward_kernel<<<grid, RW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(se3mpc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM); });
+    se3mpc_reward_kernel<<<grid, RW_WARPS * 32, RW_SMEM, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return SE3MPC_OK;

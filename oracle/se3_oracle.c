@@ -1290,7 +1290,8 @@ double se3o_reward(const se3o_params *p, const double *X, const double gate[12],
         co += coc;
     }
     for (int q = 0; q < 4; q++) {                                                   /* quad_policy.py:88-89 */
-        const double *r = pos + (N - 1 - q) * 15;
+        const int idx = (N - 1 - q >= 0) ? N - 1 - q : 2 * N - q;                    /* negative numpy index wraps (N < 4) */
+        const double *r = pos + idx * 15;
         double d[3];
         sub3(r, goal, d);
         path += dot3(d, d);

@@ -108,6 +108,39 @@ def test_reward_kernel_matches_oracle(oracle, se3):
     assert np.abs(s_g - sc_o[:, 0]).max() <= 1e-12 and np.array_equal(co_g, sc_o[:, 1].astype(np.int32))
 
 
+def test_reward_kernel_ragged_batches_and_unaligned_trajectories(oracle, se3):
+    """The stand-alone reward kernel fetches each trajectory chunk with a 16-byte-granular bulk copy from the aligned-down
+    address: odd batch sizes (X ends 8 bytes off a 16-byte boundary: the tail fix-up path), a base pointer that is only 8-byte
+    aligned, partially filled warps and a horizon whose last chunk is short must all give the oracle's numbers."""
+    from tests.test_oracle_kkt_reward import _random_traj
+    rng = np.random.default_rng(10)
+    p = oracle.default_params()
+    pool = np.stack([_random_traj(rng) for _ in range(131)])
+    sc = sample_scenarios(131, 103)
+    want = np.array([oracle.reward(p, pool[i], sc["gate"][i], sc["goal"][i]) for i in range(131)])
+    for B in (1, 3, 31, 33, 64, 97, 131):
+        for shift in (0, 1):
+            flat = torch.empty(B * 51 * 13 + shift, dtype=torch.float64, device="cuda")      # exact-size allocation
+            Xd = flat[shift:].view(B, 51, 13)
+            Xd.copy_(_t(pool[:B]))
+            assert Xd.data_ptr() % 16 == 8 * shift
+            got = se3.ops.reward(Xd, _t(sc["gate"][:B]), _t(sc["goal"][:B]))
+            torch.cuda.synchronize()
+            assert np.abs(got["reward"].cpu().numpy() - want[:B, 0]).max() <= 1e-9, (B, shift)
+            assert np.abs(got["collision"].cpu().numpy() - want[:B, 1]).max() <= 1e-12, (B, shift)
+            assert np.array_equal(got["co"].cpu().numpy(), want[:B, 3].astype(np.int32)), (B, shift)
+    # short horizons: N=2 (3 stages: one chunk), N=5 (6 stages: a full chunk of 4 and a short one)
+    for N in (2, 5):
+        pn = oracle.default_params(N=N)
+        ps = se3.default_params(N=N)
+        Xs = pool[:37, :N + 1].copy()
+        w = np.array([oracle.reward(pn, Xs[i], sc["gate"][i], sc["goal"][i]) for i in range(37)])
+        g = se3.ops.reward(_t(Xs), _t(sc["gate"][:37]), _t(sc["goal"][:37]), params=ps)
+        torch.cuda.synchronize()
+        assert np.abs(g["reward"].cpu().numpy() - w[:, 0]).max() <= 1e-9, N
+        assert np.array_equal(g["co"].cpu().numpy(), w[:, 3].astype(np.int32)), N
+
+
 def test_objective_and_sol_gradient_match_oracle(oracle, se3):
     sc = sample_scenarios(6, 103)
     p = oracle.default_params()
