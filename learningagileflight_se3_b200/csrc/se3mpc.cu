@@ -69,20 +69,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(
         if (lane == 0) pb = atomicAdd(a.ticket, 1u);
         pb = __shfl_sync(0xffffffffu, pb, 0);
         if (pb >= (unsigned)a.nprob) break;
-        if (a.order) pb = (unsigned)a.order[pb];
+        if (a.order) pb = (unsigned)se3::uni((int)a.order[pb]);      // (a loaded value is not provably warp-uniform: se3mpc_core.cuh, uni())
 
         // ---- instance (uniform registers) ----
         int src = (int)pb, variant = 0;
         if (a.mode == MODE_SOLGRAD) { src = (int)pb / 9; variant = (int)pb % 9; }
         se3::Instance in;
-        for (int i = 0; i < 13; i++) in.x0[i] = a.x0[(size_t)src * 13 + i];
+        // (loaded values are not provably warp-uniform for ptxas; the branches in round1 / rd2quat / the libm slow paths behind
+        //  them would count as divergent and drag every phase into divergence-safe code: se3mpc_core.cuh, uni())
+        for (int i = 0; i < 13; i++) in.x0[i] = se3::uni(a.x0[(size_t)src * 13 + i]);
         double ang[4];
         for (int i = 0; i < 3; i++) {
-            in.goal[i] = a.goal[(size_t)src * 3 + i];
-            in.tra_pos[i] = a.tra_pos[(size_t)src * 3 + i];
+            in.goal[i] = se3::uni(a.goal[(size_t)src * 3 + i]);
+            in.tra_pos[i] = se3::uni(a.tra_pos[(size_t)src * 3 + i]);
         }
-        for (int i = 0; i < a.att_dim; i++) ang[i] = a.tra_ang[(size_t)src * a.att_dim + i];
-        double t = a.t[src];
+        for (int i = 0; i < a.att_dim; i++) ang[i] = se3::uni(a.tra_ang[(size_t)src * a.att_dim + i]);
+        double t = se3::uni(a.t[src]);
         bool with_ulast = (a.ulast != nullptr);
         int round_t = a.round_t;
         if (a.mode == MODE_SOLGRAD) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(
         if (a.att_dim == 4) { for (int i = 0; i < 4; i++) in.tra_q[i] = ang[i]; }
         else se3::rd2quat(ang, in.tra_q);
         in.t_tra = round_t ? se3::round1(t) : t;
-        for (int j = 0; j < 4; j++) in.ulast[j] = with_ulast ? a.ulast[(size_t)src * 4 + j] : 0.0;
+        for (int j = 0; j < 4; j++) in.ulast[j] = with_ulast ? se3::uni(a.ulast[(size_t)src * 4 + j]) : 0.0;
         in.xinit = a.Xinit ? a.Xinit + (size_t)pb * (N + 1) * 13 : nullptr;
         in.uinit = a.Uinit ? a.Uinit + (size_t)pb * N * 4 : nullptr;
 
