@@ -462,7 +462,7 @@ int ctas_per_sm_for(int nproblems)
     static const int forced = [] { const char *e = getenv("SE3MPC_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     if (forced >= 1 && forced <= CTAS_PER_SM) return forced;
     const int full = num_sms() * CTAS_PER_SM * WARPS_PER_CTA;
-    return (CTAS_PER_SM > 2 && nproblems <= 5 * full) ? 2 : CTAS_PER_SM;
+    return (CTAS_PER_SM > 2 && nproblems <= 4 * full) ? 2 : CTAS_PER_SM;
 }
 
 int slots_for(int nproblems)
