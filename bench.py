@@ -44,7 +44,7 @@ W_SOLVE = N_H * 1124.0
 W_EVAL = N_H * 600.0
 W_LS = N_H * 150.0
 # DRAM bytes per problem of se3mpc_solve_kernel from the committed ncu capture (profiles/README.md): slot traffic (records, factors)
-NCU_DRAM_BYTES_PER_PROBLEM = 29.7e6
+NCU_DRAM_BYTES_PER_PROBLEM = 26.8e6
 NCU_REWARD_DRAM_BYTES_PER_TRAJECTORY = 6495.0     # se3mpc_reward_kernel, same source (5456 algorithmic)
 
 
