@@ -173,6 +173,23 @@ int se3mpc_sol_gradient_host(const se3mpc_params *p, int B, const double *x0, co
 /* frees the staging buffers the *_host entry points cache */
 void se3mpc_host_release(void);
 
+/* ---- diagnostics (used by tests/: the DEVICE code of the derivative tables, the Riccati step and the libm-free helpers) ----
+ * se3mpc_kkt_step_device: ONE Newton step of the interior-point method from a caller-supplied iterate, for B independent iterates of
+ *   horizon N: w[B][17N+13] in the reference's ordering [x0,u0,x1,u1,...,xN] (quad_OC.py:125-158), lam[B][13N] (multipliers of
+ *   g_k = x_k + dt f - x_{k+1}, quad_OC.py:162), zL / zU [B][17N+13] (bound multipliers; only the entries of u_k and of omega_k, k >= 1,
+ *   are read).  tra_q[B][4] is the traversal quaternion, t[B] is used as given.  Runs the same device functions as the solver
+ *   (prepare_stages, riccati_factor on DMMA tiles, riccati_forward) and returns dw[B][17N+13], lam_plus[B][13N], ok[B] (1 iff the KKT
+ *   matrix has inertia (n, m, 0) for this delta_w).  stage_dump (optional) [B][16*28 + 24*24]: the dense stage matrices of stage
+ *   `dump_stage` exactly as the factor sweep sees them: Rb = [A | 0 | B | c] (16 x 28, columns 0..12, 16..19, 20) followed by
+ *   Qa (24 x 24: rows/cols 0..12 x, 16..19 u, 20 gradient row) -- Hessian of the Lagrangian incl. Sigma and delta_w.
+ * se3mpc_device_math_device: out[n][8] = [ddiv(a,b), dsqrt(|a|), round1(a), rd2quat(a,b,c)(4), 0] with the device variants of the
+ *   helpers (the CPU emulation tier runs their libm alternates), a/b/c = in[n][3]. */
+int se3mpc_kkt_step_device(const se3mpc_params *p, int B, const double *goal, const double *tra_pos, const double *tra_q,
+                           const double *t, const double *ulast, const double *w, const double *lam, const double *zL,
+                           const double *zU, double mu, double delta_w, double obj_factor, double *dw, double *lam_plus,
+                           int32_t *ok, int dump_stage, double *stage_dump, void *workspace, size_t workspace_bytes, void *stream);
+int se3mpc_device_math_device(int n, const double *in3, double *out8, void *stream);
+
 /* FP64 FMA-pipe peak probe (dependent-free DFMA chains on every SM): the denominator of the solver's roofline.
  * Enqueues one launch; *flops_per_launch = FLOPs it performs (2 per FMA).  Time it with CUDA events. */
 int se3mpc_fp64_probe_device(int iters, double *sink, void *stream, double *flops_per_launch);

@@ -294,11 +294,15 @@ __global__ void __launch_bounds__(RW_WARPS * 32, RW_CTAS) se3mpc_reward_kernel(c
                 const int shift = (int)((reinterpret_cast<size_t>(a.X + off) >> 3) & 1);
                 int n = (cnt + shift + 1) & ~1;
                 if (off - shift + n > total) n -= 2;                        // never read past the end of X (tail fixed up by the consumer)
-                const unsigned dst = smem_u32(buf + (g % RW_NBUF) * 32 * RW_STRIDE + row0);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n * 8) : "memory");
+                // ... nor before its start: an X that is only 8-byte aligned (a view such as X[1:]) has shift = 1 at off = 0; the copy
+                // then starts one 16-byte unit later and the consumer fetches the first double by hand
+                const int head = (off == 0 && shift == 1) ? 2 : 0;
+                n -= head;
+                const unsigned dst = smem_u32(buf + (g % RW_NBUF) * 32 * RW_STRIDE + row0 + head);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n > 0 ? n * 8 : 0) : "memory");
                 if (n > 0)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst), "l"(a.X + off - shift), "r"(n * 8), "r"(bar) : "memory");
+                                 ::"r"(dst), "l"(a.X + off + head - shift), "r"(n * 8), "r"(bar) : "memory");
             } else {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
             }
@@ -327,8 +331,14 @@ __global__ void __launch_bounds__(RW_WARPS * 32, RW_CTAS) se3mpc_reward_kernel(c
                 const int shift = (int)((reinterpret_cast<size_t>(a.X + off) >> 3) & 1);
                 double *cur = buf + (gch % RW_NBUF) * 32 * RW_STRIDE + row0 + shift;
                 const int n = (cnt + shift + 1) & ~1;
-                if (off - shift + n > total)                                 // the copy stopped 16 bytes early: last double(s) by hand
+                bool patched = false;
+                if (off - shift + n > total) {                               // the copy stopped 16 bytes early: last double(s) by hand
                     for (int i = n - 2 - shift; i < cnt; i++) cur[i] = __ldg(a.X + off + i);
+                    patched = true;
+                }
+                if (off == 0 && shift == 1) { cur[0] = __ldg(a.X); patched = true; }      // the copy started 16 bytes late (see issue())
+                // generic-proxy stores into a buffer that a later bulk copy (async proxy) overwrites: order them before it
+                if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll 1
                 for (int q = 0; q * 13 < cnt; q++) {
                     double x[13];
@@ -418,6 +428,113 @@ __global__ void se3mpc_solgrad_epilogue(int B, const double *rew9, const double 
         for (int i = 0; i < 9; i++) status9[(size_t)b * 9 + i] = st_in[(size_t)b * 9 + i];
 }
 
+
+// ---- diagnostics: one Newton step from a given iterate (tests; mirrors tests/emu se3emu_kkt_step and the oracle's se3o_kkt_step) ----
+struct StepArgs {
+    se3mpc_params par;
+    int B, dump_stage;
+    const double *goal, *tra_pos, *tra_q, *t, *ulast, *w, *lam, *zL, *zU;
+    double mu, delta_w, obj_factor;
+    double *dw, *lam_plus, *dump;
+    int32_t *ok;
+    double *slots;
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) se3mpc_kkt_step_kernel(const __grid_constant__ StepArgs a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) se3::make_lane_tab(lane, reinterpret_cast<se3::LaneTab *>(se3_smem_raw)[lane]);
+    __syncthreads();
+    const int pb = blockIdx.x * WARPS_PER_CTA + warp;
+    if (pb >= a.B) return;
+    se3::Ctx c;
+    c.sm = reinterpret_cast<se3::WarpSmem *>(se3_smem_raw + se3::LTAB_BYTES) + warp;
+    c.lt = reinterpret_cast<const se3::LaneTab *>(se3_smem_raw);
+    c.ws = a.slots + (size_t)pb * se3::SLOT_DOUBLES;
+    se3::WarpSmem &sm = SE3_SMEM(c);
+    se3::Prob &P = sm.P;
+    const int N = a.par.N, nw = 17 * N + 13;
+    se3::prob_from_params(a.par, P);
+    for (int i = 0; i < 3; i++) { P.goal[i] = se3::uni(a.goal[(size_t)pb * 3 + i]); P.ptra[i] = se3::uni(a.tra_pos[(size_t)pb * 3 + i]); }
+    for (int j = 0; j < 4; j++) P.ulast[j] = a.ulast ? se3::uni(a.ulast[(size_t)pb * 4 + j]) : 0.0;
+    P.ttra = se3::uni(a.t[pb]);
+    double tq[4];
+    for (int i = 0; i < 4; i++) tq[i] = se3::uni(a.tra_q[(size_t)pb * 4 + i]);
+    se3::att_form(tq, P.Nq, &P.s0);
+    P.sf = a.obj_factor;
+    if (lane == 0) { sm.nfact = 0; sm.nfilt = 0; }
+    __syncwarp();
+    const double *w = a.w + (size_t)pb * nw, *zL = a.zL + (size_t)pb * nw, *zU = a.zU + (size_t)pb * nw, *lam = a.lam + (size_t)pb * 13 * N;
+    for (int e = lane; e < se3::R_END * se3::NS; e += 32) c.ws[e] = 0.0;
+    __syncwarp();
+    for (int s = lane; s <= N; s += 32) {
+        for (int i = 0; i < 13; i++) se3::row(c, se3::R_X + i)[s] = w[s * 17 + i];
+        for (int j = 0; j < 3; j++) { se3::row(c, se3::R_ZLW + j)[s] = zL[s * 17 + 10 + j]; se3::row(c, se3::R_ZUW + j)[s] = zU[s * 17 + 10 + j]; }
+        if (s < N) {
+            for (int j = 0; j < 4; j++) {
+                se3::row(c, se3::R_U + j)[s] = w[s * 17 + 13 + j];
+                se3::row(c, se3::R_ZLU + j)[s] = zL[s * 17 + 13 + j];
+                se3::row(c, se3::R_ZUU + j)[s] = zU[s * 17 + 13 + j];
+            }
+            for (int i = 0; i < 13; i++) se3::row(c, se3::R_LAM + i)[s] = lam[s * 13 + i];
+            const double d = P.dt * s - P.ttra;
+            se3::row(c, se3::R_GAM)[s] = a.par.gamma_amp * exp(-a.par.gamma_rate * d * d);
+        }
+    }
+    __syncwarp();
+    se3::init_AB(c);
+    double th, ci;
+    se3::eval_constraints(c, &th, &ci);
+    const int ok = se3::uni(se3::riccati(c, SE3_MODE_EXACT, 1, 1, a.delta_w, a.mu, se3::R_C, se3::R_DX, se3::R_DU, se3::R_LAMP));
+    double *dw = a.dw + (size_t)pb * nw, *lp = a.lam_plus + (size_t)pb * 13 * N;
+    for (int s = lane; s <= N; s += 32) {
+        for (int i = 0; i < 13; i++) dw[s * 17 + i] = se3::row(c, se3::R_DX + i)[s];
+        if (s < N) {
+            for (int j = 0; j < 4; j++) dw[s * 17 + 13 + j] = se3::row(c, se3::R_DU + j)[s];
+            for (int i = 0; i < 13; i++) lp[s * 13 + i] = se3::row(c, se3::R_LAMP + i)[s];
+        }
+    }
+    if (lane == 0 && a.ok) a.ok[pb] = ok;
+    if (a.dump && a.dump_stage >= 0 && a.dump_stage < N) {
+        // the stage matrices as the factor sweep's S1 builds them: constant parts (init_AB), then the packed record through the lane table
+        __syncwarp();
+        se3::init_AB(c);
+        double *sbase = reinterpret_cast<double *>(&sm);
+        const se3::LaneTab t = SE3_LTAB(c)[lane];
+        const se3::GP R = se3::rec(c, a.dump_stage);
+        const double r0 = R[lane], r1 = R[32 + lane], r2 = R[64 + lane], r3 = R[96 + lane];
+        sbase[t.f0] = r0;
+        const double w1 = r1 + (t.addd[1] ? a.delta_w : 0.0), w2 = r2 + (t.addd[2] ? a.delta_w : 0.0);
+        for (int d = 0; d < 4; d++) {
+            if (t.f1[d] >= 0) sbase[t.f1[d]] = w1;
+            if (t.f2[d] >= 0) sbase[t.f2[d]] = w2;
+        }
+        if (t.f3 >= 0) sbase[t.f3] = r3;
+        if (lane < 13) sm.Rb[lane * se3::SR + se3::EH] = se3::row(c, se3::R_C + lane)[a.dump_stage];
+        __syncwarp();
+        double *o = a.dump + (size_t)pb * (16 * se3::SR + 24 * se3::SQ);
+        for (int e = lane; e < 16 * se3::SR; e += 32) o[e] = sm.Rb[e];
+        for (int e = lane; e < 24 * se3::SQ; e += 32) {
+            const int i = e / se3::SQ, j = e % se3::SQ;
+            o[16 * se3::SR + e] = (i < 16 && j >= se3::FXO) ? 0.0 : sm.Qa[e];      // (the FX block is sweep state, not part of the stage Hessian)
+        }
+    }
+}
+
+__global__ void se3mpc_device_math_kernel(int n, const double *in3, double *out8)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = in3[(size_t)i * 3], b = in3[(size_t)i * 3 + 1], cc = in3[(size_t)i * 3 + 2];
+    double *o = out8 + (size_t)i * 8;
+    o[0] = se3::ddiv(a, b);
+    o[1] = se3::dsqrt(fabs(a));
+    o[2] = se3::round1(a);
+    const double v[3] = {a, b, cc};
+    se3::rd2quat(v, o + 3);
+    o[7] = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
@@ -451,6 +568,32 @@ int num_sms()
 }
 
 constexpr size_t HDR_BYTES = 256;
+constexpr size_t SOLVER_SMEM = se3::LTAB_BYTES + sizeof(se3::WarpSmem) * WARPS_PER_CTA;
+constexpr int MAX_DEVICES = 64;
+
+// Function attributes are per device (per primary context): the opt-in to more than 48 KB of dynamic shared memory has to be made on
+// every device a launch goes to, not once per process.  Done on first use of each device, return codes checked.
+int device_setup()
+{
+    static std::mutex mu;
+    static bool done[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(SE3MPC_ERR_CUDA, "cudaGetDevice", e);
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(SE3MPC_ERR_INVALID, "device index out of range");
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return SE3MPC_OK;
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<2>)", e);
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS>)", e);
+    if ((e = cudaFuncSetAttribute(se3mpc_kkt_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_kkt_step_kernel)", e);
+    if ((e = cudaFuncSetAttribute(se3mpc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM)) != cudaSuccess)
+        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_reward_kernel)", e);
+    done[dev] = true;
+    return SE3MPC_OK;
+}
 
 // Resident CTAs per SM for a launch of `nproblems`; the solver kernel is instantiated for 2 (255 registers) and for CTAS_PER_SM
 // (168 registers).  Fewer, fatter warps mean a lower per-problem latency (more registers, a larger share of the instruction
@@ -535,12 +678,8 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
         CK(cudaGetLastError());
         a.order = L.lpt_order;
     }
-    const size_t smem = se3::LTAB_BYTES + sizeof(se3::WarpSmem) * WARPS_PER_CTA;
-    static std::once_flag once;
-    std::call_once(once, [&] {
-        cudaFuncSetAttribute(se3mpc_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    });
+    const size_t smem = SOLVER_SMEM;
+    { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) return rc_attr; }
     const int grid = L.nslots / WARPS_PER_CTA;
     if (ctas_per_sm_for(nprob) <= 2) se3mpc_solve_kernel<2><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
     else se3mpc_solve_kernel<CTAS_PER_SM><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
@@ -618,8 +757,7 @@ int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const d
     int grid = ((B + 31) / 32 + RW_WARPS - 1) / RW_WARPS;       // one thread per trajectory, RW_WARPS warps per CTA
     const int cap = num_sms() * RW_CTAS * 2;
     if (grid > cap) grid = cap;
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(se3mpc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM); });
+    { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) return rc_attr; }
     se3mpc_reward_kernel<<<grid, RW_WARPS * 32, RW_SMEM, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches++;
     CK(cudaGetLastError());
@@ -635,6 +773,41 @@ int se3mpc_fp64_probe_device(int iters, double *sink, void *stream, double *flop
     g_launches++;
     CK(cudaGetLastError());
     if (flops_per_launch) *flops_per_launch = 512.0 * 8.0 * (double)iters * 8.0 * (double)grid;      // 512 flop per DMMA, 8 chains, 8 warps per CTA
+    return SE3MPC_OK;
+}
+
+int se3mpc_kkt_step_device(const se3mpc_params *p, int B, const double *goal, const double *tra_pos, const double *tra_q,
+                           const double *t, const double *ulast, const double *w, const double *lam, const double *zL,
+                           const double *zU, double mu, double delta_w, double obj_factor, double *dw, double *lam_plus,
+                           int32_t *ok, int dump_stage, double *stage_dump, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !goal || !tra_pos || !tra_q || !t || !w || !lam || !zL || !zU || !dw || !lam_plus || !(mu > 0))
+        return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0) return SE3MPC_OK;
+    const size_t need = (size_t)B * se3::SLOT_DOUBLES * sizeof(double);
+    if (!workspace || workspace_bytes < need) return fail(SE3MPC_ERR_WORKSPACE, "workspace too small (B * slot bytes)");
+    { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) return rc_attr; }
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.par = *p; a.B = B; a.dump_stage = dump_stage;
+    a.goal = goal; a.tra_pos = tra_pos; a.tra_q = tra_q; a.t = t; a.ulast = ulast; a.w = w; a.lam = lam; a.zL = zL; a.zU = zU;
+    a.mu = mu; a.delta_w = delta_w; a.obj_factor = obj_factor; a.dw = dw; a.lam_plus = lam_plus; a.dump = stage_dump; a.ok = ok;
+    a.slots = static_cast<double *>(workspace);
+    se3mpc_kkt_step_kernel<<<(B + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, SOLVER_SMEM, static_cast<cudaStream_t>(stream)>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
+int se3mpc_device_math_device(int n, const double *in3, double *out8, void *stream)
+{
+    if (n < 0 || !in3 || !out8) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (n == 0) return SE3MPC_OK;
+    se3mpc_device_math_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, in3, out8);
+    g_launches++;
+    CK(cudaGetLastError());
     return SE3MPC_OK;
 }
 
@@ -707,9 +880,24 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+// Staging buffers and the stream of the host-buffer entry points, one set per device: a buffer or stream created while device A was
+// current must not be used after the caller switched to device B (ops.py wraps calls in torch.cuda.device(dev)).
 std::mutex g_host_mu;
-DevBuf g_in, g_out, g_ws;
-cudaStream_t g_stream = nullptr;
+struct HostCtx { DevBuf in, out, ws; cudaStream_t stream = nullptr; };
+HostCtx g_host[MAX_DEVICES];
+HostCtx *host_ctx()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    return &g_host[dev];
+}
+#define HOST_CTX()                                                                         \
+    HostCtx *hc_ = host_ctx();                                                             \
+    if (!hc_) return fail(SE3MPC_ERR_CUDA, "cudaGetDevice failed or device index out of range"); \
+    DevBuf &g_in = hc_->in, &g_out = hc_->out, &g_ws = hc_->ws;                            \
+    cudaStream_t &g_stream = hc_->stream;                                                  \
+    (void)g_in; (void)g_out; (void)g_ws;                                                   \
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking))
 
 struct Arena {
     unsigned char *base;
@@ -728,7 +916,7 @@ int host_common(const se3mpc_params *p, int mode, int B, const double *x0, const
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
     std::lock_guard<std::mutex> lk(g_host_mu);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    HOST_CTX();
     const int N = p->N;
     const int nprob = (mode == MODE_SOLGRAD) ? 9 * B : B;
     const size_t in_bytes = pad((size_t)B * 13 * 8) + 2 * pad((size_t)B * 3 * 8) + pad((size_t)B * 4 * 8) + pad((size_t)B * 12 * 8) + pad((size_t)B * 8) + pad((size_t)B * 4 * 8);
@@ -826,7 +1014,7 @@ int se3mpc_reward_host(const se3mpc_params *p, int B, const double *X, const dou
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
     std::lock_guard<std::mutex> lk(g_host_mu);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    HOST_CTX();
     const int N = p->N;
     int rc;
     const size_t xb = (size_t)B * (N + 1) * 13 * 8;
@@ -856,7 +1044,7 @@ int se3mpc_collis_det_host(int B, int horizon, const double *V, const double *ga
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
     std::lock_guard<std::mutex> lk(g_host_mu);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    HOST_CTX();
     int rc;
     const size_t vb = (size_t)B * (horizon + 1) * 3 * 8;
     if ((rc = g_in.ensure(pad(vb) + pad((size_t)B * 12 * 8))) != SE3MPC_OK) return rc;
@@ -916,7 +1104,7 @@ int se3mpc_rotor_positions_host(int nstates, double wing_len, const double *X, d
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (nstates == 0) return SE3MPC_OK;
     std::lock_guard<std::mutex> lk(g_host_mu);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    HOST_CTX();
     int rc;
     if ((rc = g_in.ensure(pad((size_t)nstates * 13 * 8))) != SE3MPC_OK) return rc;
     if ((rc = g_out.ensure(pad((size_t)nstates * 15 * 8))) != SE3MPC_OK) return rc;
@@ -937,7 +1125,7 @@ int se3mpc_gate_frame_host(int B, const double *gate, const double *velo, const 
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
     std::lock_guard<std::mutex> lk(g_host_mu);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    HOST_CTX();
     int rc;
     if ((rc = g_in.ensure(pad((size_t)B * 12 * 8) + 2 * pad((size_t)B * 3 * 8) + 2 * pad((size_t)B * 8) + pad((size_t)B * 13 * 8))) != SE3MPC_OK) return rc;
     if ((rc = g_out.ensure(pad((size_t)B * 18 * 8) + pad((size_t)B * 12 * 8))) != SE3MPC_OK) return rc;
@@ -966,7 +1154,7 @@ int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps,
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0 || nsteps == 0) return SE3MPC_OK;
     std::lock_guard<std::mutex> lk(g_host_mu);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    HOST_CTX();
     int rc;
     if ((rc = g_in.ensure(pad((size_t)B * 4 * 8))) != SE3MPC_OK) return rc;
     if ((rc = g_out.ensure(pad((size_t)B * 13 * 8))) != SE3MPC_OK) return rc;
@@ -984,8 +1172,16 @@ int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps,
 void se3mpc_host_release(void)
 {
     std::lock_guard<std::mutex> lk(g_host_mu);
-    g_in.release(); g_out.release(); g_ws.release();
-    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    int cur = 0, n = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess || cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int d = 0; d < n && d < MAX_DEVICES; d++) {
+        HostCtx &h = g_host[d];
+        if (!h.in.p && !h.out.p && !h.ws.p && !h.stream) continue;
+        cudaSetDevice(d);
+        h.in.release(); h.out.release(); h.ws.release();
+        if (h.stream) { cudaStreamDestroy(h.stream); h.stream = nullptr; }
+    }
+    cudaSetDevice(cur);
 }
 
 }  // extern "C"

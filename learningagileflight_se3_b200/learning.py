@@ -57,29 +57,63 @@ def rl_gradients(inputs, outs, params: Optional[Params] = None):
     return g[:, 0:7], g[:, 7], st9
 
 
-def rl_step(model: Callable, optimizer, inputs, mode: str = "sequential", params: Optional[Params] = None):
-    """One mini-batch of the RL loop (deep_learning.py:44-88).  `model` maps a 9-vector (or [B,9] for mode="batched") to 7 outputs.
-    Returns the rewards of the batch (n_gra[j][7])."""
+def _model_batch(model: Callable, inputs: np.ndarray) -> torch.Tensor:
+    """DNN outputs [B,7] for inputs[B,9] in ONE forward pass when the model can take a batch, else one call per sample.  The
+    reference's network transposes its input (quad_nn.py:118: `S.t()`, "column 2D tensor"), i.e. it takes [9,B]; other models take
+    [B,9].  Which form (if any) reproduces the per-sample outputs is probed once on the first two samples."""
+    B = inputs.shape[0]
+    single = [model(inputs[j]).reshape(7) for j in range(min(B, 2))]
+    if B >= 2:
+        with torch.no_grad():
+            ref2 = torch.stack([s.detach() for s in single])
+            form = None
+            for name, arg in (("rows", inputs[:2]), ("cols", np.ascontiguousarray(inputs[:2].T))):
+                try:
+                    o = model(arg)
+                    if isinstance(o, torch.Tensor) and o.numel() == 14 and torch.allclose(o.reshape(2, 7), ref2, rtol=1e-5, atol=1e-6):
+                        form = name
+                        break
+                except Exception:
+                    continue
+        if form is not None:
+            return model(inputs if form == "rows" else np.ascontiguousarray(inputs.T)).reshape(B, 7)
+    return torch.stack(single + [model(inputs[j]).reshape(7) for j in range(len(single), B)])
+
+
+def rl_step(model: Callable, optimizer, inputs, mode: str = "sequential", params: Optional[Params] = None, return_info: bool = False):
+    """One mini-batch of the RL loop (deep_learning.py:44-88).  `model` maps a 9-vector (and, for the batched passes, [B,9]) to 7
+    outputs.  Returns the rewards of the batch (n_gra[j][7]); with return_info also {"skipped": indices, "status9": ...}.
+
+    Samples whose 9 solves did not all converge (status > 1: the reference never reads IPOPT's status, quad_OC.py:174-175, and would
+    feed such rewards straight into Adam) or whose pseudo-gradient is not finite are SKIPPED: they take no optimizer step
+    ("sequential") / carry zero weight ("batched"), so one failed solve cannot poison the weights.  Their rewards are still returned."""
     inputs = np.asarray(inputs, dtype=np.float64).reshape(-1, 9)
     B = inputs.shape[0]
     with torch.no_grad():                                                   # deep_learning.py:52-54 (snapshot outputs)
-        outs = np.stack([np.asarray(model(inputs[j]).detach().cpu().numpy(), dtype=np.float64).reshape(7) for j in range(B)])
-    Dp, reward, _ = rl_gradients(inputs, outs, params)                      # deep_learning.py:63-72, one launch instead of B processes
+        outs = np.asarray(_model_batch(model, inputs).detach().cpu().numpy(), dtype=np.float64).reshape(B, 7)
+    Dp, reward, st9 = rl_gradients(inputs, outs, params)                    # deep_learning.py:63-72, one launch instead of B processes
+    good = np.all(np.asarray(st9) <= 1, axis=1) & np.all(np.isfinite(Dp), axis=1) & np.isfinite(reward)
     if mode == "sequential":
         for j in range(B):                                                  # deep_learning.py:75-81
+            if not good[j]:
+                continue
             outputs = model(inputs[j])
             loss = myloss_batch(outputs.reshape(1, 7), Dp[j:j + 1]).sum()
             optimizer.zero_grad()
             loss.backward()
             optimizer.step()
     elif mode == "batched":
-        outputs = torch.stack([model(inputs[j]).reshape(7) for j in range(B)])
-        loss = myloss_batch(outputs, Dp).mean()
-        optimizer.zero_grad()
-        loss.backward()
-        optimizer.step()
+        if good.any():
+            outputs = _model_batch(model, inputs)                           # one forward pass for the mini-batch
+            wgt = torch.as_tensor(good.astype(np.float64), dtype=outputs.dtype, device=outputs.device)
+            loss = (myloss_batch(outputs, np.where(good[:, None], Dp, 0.0)) * wgt).sum() / wgt.sum()
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
     else:
         raise ValueError(mode)
+    if return_info:
+        return reward, {"skipped": np.where(~good)[0], "status9": st9}
     return reward
 
 

@@ -79,6 +79,8 @@ def solve(x0, goal, tra_pos, tra_ang, t, ulast=None, round_t=False, params: Opti
     st, cs = _stats(B, dev)
     _require_cuda(x_init, u_init)
     x_init, u_init = _c(x_init, (B, N + 1, 13)), _c(u_init, (B, N, 4))
+    if B == 0:          # empty shard: nothing to launch (the C ABI accepts B = 0 as well), empty outputs
+        return {"state_traj_opt": X, "control_traj_opt": U, "costate_traj_opt": LAM, "cost": cost, **st}
     with torch.cuda.device(dev):
         ws = _workspace(p, B, dev)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -104,6 +106,8 @@ def reward(X, gate, goal, params: Optional[Params] = None):
     r = torch.empty(B, dtype=torch.float64, device=dev)
     col, path = torch.empty_like(r), torch.empty_like(r)
     co = torch.empty(B, dtype=torch.int32, device=dev)
+    if B == 0:
+        return {"reward": r, "collision": col, "path": path, "co": co}
     with torch.cuda.device(dev):
         rc = _lib.lib().se3mpc_reward_device(C.byref(p), B, _ptr(X), _ptr(gate), _ptr(goal), _ptr(r), _ptr(col), _ptr(path), _ptr(co),
                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
@@ -123,6 +127,8 @@ def objective(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: Optional[
     X = torch.empty((B, N + 1, 13), dtype=torch.float64, device=dev) if want_traj else None
     U = torch.empty((B, N, 4), dtype=torch.float64, device=dev) if want_traj else None
     st, cs = _stats(B, dev)
+    if B == 0:
+        return {"reward": r, "cost": cost, "state_traj_opt": X, "control_traj_opt": U, **st}
     with torch.cuda.device(dev):
         ws = _workspace(p, B, dev)
         rc = _lib.lib().se3mpc_objective_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(gate), _ptr(tra_pos), _ptr(tra_ang), _ptr(t),
@@ -141,6 +147,8 @@ def sol_gradient(x0, goal, gate, tra_pos, tra_ang, t, ulast=None, params: Option
     tra_pos, tra_ang, t, ulast = _c(tra_pos, (B, 3)), _c(tra_ang, (B, 3)), _c(t, (B,)), _c(ulast, (B, 4))
     out = torch.empty((B, 8), dtype=torch.float64, device=dev)
     st9 = torch.empty((B, 9), dtype=torch.int32, device=dev)
+    if B == 0:
+        return out, st9
     with torch.cuda.device(dev):
         ws = _workspace(p, 9 * B, dev)
         rc = _lib.lib().se3mpc_sol_gradient_device(C.byref(p), B, _ptr(x0), _ptr(goal), _ptr(gate), _ptr(tra_pos), _ptr(tra_ang), _ptr(t),
@@ -317,6 +325,53 @@ def rotor_positions_host(X, wing_len):
     rc = _lib.lib().se3mpc_rotor_positions_host(X.shape[0], float(wing_len), _np_ptr(X), _np_ptr(pos))
     _lib.check(rc, "se3mpc_rotor_positions_host")
     return pos
+
+
+# ---- diagnostics (tests): the device code of one Newton step / of the libm-free helpers ------------------------------
+def kkt_step(goal, tra_pos, tra_q, t, w, lam, zL, zU, mu, delta_w, obj_factor=1.0, ulast=None, params: Optional[Params] = None,
+             dump_stage=-1):
+    """se3mpc_kkt_step_device: one interior-point Newton step from the iterates w[B,17N+13] (reference ordering), lam[B,13N],
+    zL/zU[B,17N+13].  Returns (ok[B], dw[B,17N+13], lam_plus[B,13N]) and, with dump_stage >= 0, the dense stage matrices
+    (A[B,13,13], Bm[B,13,4], c[B,13], H[B,17,17] over (x,u), g[B,17]) as the factor sweep sees them."""
+    p = params or default_params()
+    _require_cuda(goal, tra_pos, tra_q, t, w, lam, zL, zU, ulast)
+    N = p.N
+    nw = 17 * N + 13
+    B, dev = w.reshape(-1, nw).shape[0], w.device
+    goal, tra_pos, tra_q, t = _c(goal, (B, 3)), _c(tra_pos, (B, 3)), _c(tra_q, (B, 4)), _c(t, (B,))
+    w, lam, zL, zU, ulast = _c(w, (B, nw)), _c(lam, (B, 13 * N)), _c(zL, (B, nw)), _c(zU, (B, nw)), _c(ulast, (B, 4))
+    dw = torch.empty((B, nw), dtype=torch.float64, device=dev)
+    lp = torch.empty((B, 13 * N), dtype=torch.float64, device=dev)
+    ok = torch.empty(B, dtype=torch.int32, device=dev)
+    dump = torch.zeros((B, 16 * 28 + 24 * 24), dtype=torch.float64, device=dev) if dump_stage >= 0 else None
+    with torch.cuda.device(dev):
+        slot = int(_lib.lib().se3mpc_workspace_bytes(C.byref(p), 1))      # header + one slot: an upper bound of the per-iterate slot
+        ws = torch.empty(max(B, 1) * slot, dtype=torch.uint8, device=dev)
+        rc = _lib.lib().se3mpc_kkt_step_device(C.byref(p), B, _ptr(goal), _ptr(tra_pos), _ptr(tra_q), _ptr(t), _ptr(ulast), _ptr(w), _ptr(lam),
+                                               _ptr(zL), _ptr(zU), float(mu), float(delta_w), float(obj_factor), _ptr(dw), _ptr(lp), _ptr(ok),
+                                               int(dump_stage), _ptr(dump), _ptr(ws), ws.numel(),
+                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_kkt_step_device")
+    if dump is None:
+        return ok, dw, lp
+    Rb = dump[:, :16 * 28].reshape(B, 16, 28)
+    Qa = dump[:, 16 * 28:].reshape(B, 24, 24)
+    idx = list(range(13)) + [16, 17, 18, 19]
+    H = Qa[:, idx][:, :, idx]
+    g = Qa[:, 20][:, idx]
+    return ok, dw, lp, {"A": Rb[:, :13, :13], "B": Rb[:, :13, 16:20], "c": Rb[:, :13, 20], "H": H, "g": g, "Qa": Qa, "Rb": Rb}
+
+
+def device_math(in3):
+    """se3mpc_device_math_device: [ddiv(a,b), dsqrt(|a|), round1(a), rd2quat(a,b,c)(4), 0] with the DEVICE variants of the helpers."""
+    _require_cuda(in3)
+    n, dev = in3.reshape(-1, 3).shape[0], in3.device
+    in3 = _c(in3, (n, 3))
+    out = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().se3mpc_device_math_device(n, _ptr(in3), _ptr(out), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_device_math_device")
+    return out
 
 
 # ---- torch custom ops: torch.ops.se3mpc.{solve,reward,objective,sol_gradient} (CUDA dispatch key only) ------

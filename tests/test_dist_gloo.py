@@ -13,7 +13,8 @@ from learningagileflight_se3_b200.dist import shard_range, sharded_call
 
 
 def _fake_op(x0, t):
-    # deterministic per-problem function with the output shapes of sol_gradient ([B,8]) and objective ([B])
+    # deterministic per-problem function with the output shapes of sol_gradient ([B,8]) and objective ([B]); like the real ops it
+    # returns EMPTY outputs for an empty shard (ops.py: B == 0 returns before any workspace / launch)
     g = torch.stack([x0[:, i % 13] * (i + 1) + t for i in range(8)], 1)
     return {"grad": g, "reward": x0.sum(1) - t, "status": (x0[:, 0] > 0).to(torch.int32)}
 
@@ -70,3 +71,16 @@ def test_sharded_results_are_invariant_to_world_size():
         got = _run(world, n)
         for k in want:
             assert np.array_equal(got[k], want[k]), (world, k)
+
+
+def test_fewer_problems_than_ranks_does_not_deadlock():
+    """n < world: some ranks own an empty shard; they must still take part in the gather (an exception before the collective
+    would leave the other ranks blocked in it until the timeout)."""
+    rng = np.random.default_rng(0)
+    for n, world in ((2, 3), (1, 2)):
+        inputs = {"x0": rng.normal(size=(n, 13)), "t": rng.uniform(2, 4, n)}
+        rng = np.random.default_rng(0)
+        want = {k: v.numpy() for k, v in _fake_op(torch.as_tensor(inputs["x0"]), torch.as_tensor(inputs["t"])).items()}
+        got = _run(world, n)
+        for k in want:
+            assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), (world, n, k)
