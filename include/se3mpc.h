@@ -148,6 +148,12 @@ int se3mpc_solve_warm_device(const se3mpc_params *p, int B, const double *x0, co
 int se3mpc_gate_frame_device(int B, const double *gate, const double *velo, const double *w, const double *t,
                              const double *state, const double *final_point, double *inputs18, double *gate_pred, void *stream);
 int se3mpc_plant_step_device(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state, void *stream);
+/* se3mpc_episode_advance: everything between two re-solves of main.py's loop in ONE launch (main.py:108 and gate.move,
+ *   quad_model.py:769-790), nsteps times: state[b] <- one Euler step of size dt with u[b] held; gate[b] (corners [12]) <- rotated about
+ *   its centroid by w[b] dt and translated by (velo[b] + noise[j][b]) dt.  noise[nsteps][B][3] or NULL.  state and gate are updated
+ *   in place; bit-identical to nsteps x (se3mpc_plant_step(1 step) ; se3mpc_gate_frame(t = dt) -> gate_pred). */
+int se3mpc_episode_advance_device(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state, double *gate,
+                                  const double *velo, const double *w, const double *noise, void *stream);
 
 /* Quadrotor.get_quadrotor_position (quad_model.py:239-276): X[nstates][13] -> pos[nstates][15] = centre of mass + the four rotor
  * tips r + R(q)^T b_i, b_i = (+-a, +-a, 0), a = wing_len * 0.5 / sqrt(2), with the reference's un-normalised quaternion. */

@@ -49,7 +49,7 @@ EXPORTS = [
     "se3mpc_sol_gradient_device", "se3mpc_solve_host", "se3mpc_reward_host", "se3mpc_collis_det_host",
     "se3mpc_objective_host", "se3mpc_sol_gradient_host", "se3mpc_host_release", "se3mpc_launch_count", "se3mpc_fp64_probe_device",
     "se3mpc_gate_frame_device", "se3mpc_gate_frame_host", "se3mpc_plant_step_device", "se3mpc_plant_step_host", "se3mpc_solve_warm_device", "se3mpc_rotor_positions_device", "se3mpc_rotor_positions_host",
-    "se3mpc_kkt_step_device", "se3mpc_device_math_device",
+    "se3mpc_kkt_step_device", "se3mpc_device_math_device", "se3mpc_episode_advance_device",
 ]
 
 
@@ -108,6 +108,8 @@ def lib():
     L.se3mpc_kkt_step_device.argtypes = [pp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd, cd, cd, vp, vp, vp, ci, vp, vp, C.c_size_t, vp]
     L.se3mpc_device_math_device.argtypes = [ci, vp, vp, vp]
     L.se3mpc_kkt_step_device.restype = L.se3mpc_device_math_device.restype = ci
+    L.se3mpc_episode_advance_device.argtypes = [pp, ci, cd, ci, vp, vp, vp, vp, vp, vp, vp]
+    L.se3mpc_episode_advance_device.restype = ci
     for f in ("se3mpc_gate_frame_device", "se3mpc_gate_frame_host", "se3mpc_plant_step_device", "se3mpc_plant_step_host"):
         getattr(L, f).restype = ci
     for f in ("se3mpc_collis_det_device", "se3mpc_collis_det_host", "se3mpc_solve_device", "se3mpc_reward_device", "se3mpc_objective_device", "se3mpc_sol_gradient_device",

@@ -217,6 +217,35 @@ __global__ void se3mpc_plant_step_kernel(const __grid_constant__ se3mpc_params p
     for (int i = 0; i < 13; i++) state[(size_t)b * 13 + i] = x[i];
 }
 
+// One MPC tick of the moving-gate closed loop between two re-solves (main.py:108 + gate.move, quad_model.py:769-790): nsteps times
+// { plant Euler step with the control held; gate rotated about its centroid by w dt and translated by (velo + noise) dt }.
+// One thread per episode, state and gate corners updated in place: replaces nsteps plant_step + nsteps gate_frame launches.
+__global__ void se3mpc_episode_advance_kernel(const __grid_constant__ se3mpc_params par, int B, double dt, int nsteps, const double *u,
+                                              double *state, double *gate, const double *velo, const double *w, const double *noise)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    se3::Prob P;
+    se3::prob_from_params(par, P);
+    double x[13], uu[4], g[12], v0[3];
+    for (int i = 0; i < 13; i++) x[i] = state[(size_t)b * 13 + i];
+    for (int j = 0; j < 4; j++) uu[j] = u[(size_t)b * 4 + j];
+    for (int i = 0; i < 12; i++) g[i] = gate[(size_t)b * 12 + i];
+    for (int d = 0; d < 3; d++) v0[d] = velo[(size_t)b * 3 + d];
+    const double wb = w[b];
+    for (int j = 0; j < nsteps; j++) {
+        se3::plant_steps(P, dt, 1, uu, x);
+        double v[3] = {v0[0], v0[1], v0[2]}, Pn[4][3], cen[3];
+        if (noise)
+            for (int d = 0; d < 3; d++) v[d] = v0[d] + noise[((size_t)j * B + b) * 3 + d];
+        se3::gate_predict(g, v, wb, dt, Pn, cen);
+        for (int i = 0; i < 4; i++)
+            for (int d = 0; d < 3; d++) g[i * 3 + d] = Pn[i][d];
+    }
+    for (int i = 0; i < 13; i++) state[(size_t)b * 13 + i] = x[i];
+    for (int i = 0; i < 12; i++) gate[(size_t)b * 12 + i] = g[i];
+}
+
 // quad_model.py:239-276 get_quadrotor_position: centre of mass + the four rotor tips of every state, one thread per state
 __global__ void se3mpc_rotor_positions_kernel(int nstates, double arm, const double *X, double *pos)
 {
@@ -429,7 +458,7 @@ __global__ void se3mpc_solgrad_epilogue(int B, const double *rew9, const double 
 }
 
 
-// ---- diagnostics: one Newton step from a given iterate (tests; mirrors tests/emu se3emu_kkt_step and the oracle's se3o_kkt_step) ----
+// ---- diagnostics: one Newton step from a given iterate (tests; same contract as the host emulation's and the CPU checker's one-step entry points) ----
 struct StepArgs {
     se3mpc_params par;
     int B, dump_stage;
@@ -880,19 +909,30 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-// Staging buffers and the stream of the host-buffer entry points, one set per device: a buffer or stream created while device A was
-// current must not be used after the caller switched to device B (ops.py wraps calls in torch.cuda.device(dev)).
-std::mutex g_host_mu;
-struct HostCtx { DevBuf in, out, ws; cudaStream_t stream = nullptr; };
-HostCtx g_host[MAX_DEVICES];
-HostCtx *host_ctx()
+// Staging buffers and the stream of the host-buffer entry points: HOST_LANES independent sets per device.  Per device, because a
+// buffer or stream created while device A was current must not be used after the caller switched to device B (ops.py wraps calls in
+// torch.cuda.device(dev)); several lanes, so that host threads calling concurrently (ctypes releases the GIL) each get their own
+// stream + workspace and their launches overlap on the device -- the straggler tail of one batch is then filled by the next batch.
+constexpr int HOST_LANES = 4;
+struct HostCtx { std::mutex mu; DevBuf in, out, ws; cudaStream_t stream = nullptr; };
+HostCtx g_host[MAX_DEVICES][HOST_LANES];
+struct HostLease {
+    HostCtx *h = nullptr;
+    ~HostLease() { if (h) h->mu.unlock(); }
+};
+HostCtx *host_ctx(HostLease &lease)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
-    return &g_host[dev];
+    for (int l = 0; l < HOST_LANES; l++)
+        if (g_host[dev][l].mu.try_lock()) { lease.h = &g_host[dev][l]; return lease.h; }
+    g_host[dev][0].mu.lock();           // every lane busy: queue behind lane 0
+    lease.h = &g_host[dev][0];
+    return lease.h;
 }
 #define HOST_CTX()                                                                         \
-    HostCtx *hc_ = host_ctx();                                                             \
+    HostLease lease_;                                                                      \
+    HostCtx *hc_ = host_ctx(lease_);                                                       \
     if (!hc_) return fail(SE3MPC_ERR_CUDA, "cudaGetDevice failed or device index out of range"); \
     DevBuf &g_in = hc_->in, &g_out = hc_->out, &g_ws = hc_->ws;                            \
     cudaStream_t &g_stream = hc_->stream;                                                  \
@@ -915,7 +955,6 @@ int host_common(const se3mpc_params *p, int mode, int B, const double *x0, const
     if (mode != MODE_SOLVE && !gate) return fail(SE3MPC_ERR_INVALID, "invalid argument");
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
-    std::lock_guard<std::mutex> lk(g_host_mu);
     HOST_CTX();
     const int N = p->N;
     const int nprob = (mode == MODE_SOLGRAD) ? 9 * B : B;
@@ -1013,7 +1052,6 @@ int se3mpc_reward_host(const se3mpc_params *p, int B, const double *X, const dou
     if (!params_ok(p) || B < 0 || !X || !gate || !goal || !reward) return fail(SE3MPC_ERR_INVALID, "invalid argument");
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
-    std::lock_guard<std::mutex> lk(g_host_mu);
     HOST_CTX();
     const int N = p->N;
     int rc;
@@ -1043,7 +1081,6 @@ int se3mpc_collis_det_host(int B, int horizon, const double *V, const double *ga
     if (B < 0 || horizon < 1 || !V || !gate || !score) return fail(SE3MPC_ERR_INVALID, "invalid argument");
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
-    std::lock_guard<std::mutex> lk(g_host_mu);
     HOST_CTX();
     int rc;
     const size_t vb = (size_t)B * (horizon + 1) * 3 * 8;
@@ -1087,6 +1124,18 @@ int se3mpc_plant_step_device(const se3mpc_params *p, int B, double dt, int nstep
     return SE3MPC_OK;
 }
 
+int se3mpc_episode_advance_device(const se3mpc_params *p, int B, double dt, int nsteps, const double *u, double *state, double *gate,
+                                  const double *velo, const double *w, const double *noise, void *stream)
+{
+    if (!params_ok(p) || B < 0 || !(dt > 0) || nsteps < 0 || !u || !state || !gate || !velo || !w) return fail(SE3MPC_ERR_INVALID, "invalid argument");
+    if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
+    if (B == 0 || nsteps == 0) return SE3MPC_OK;
+    se3mpc_episode_advance_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, B, dt, nsteps, u, state, gate, velo, w, noise);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SE3MPC_OK;
+}
+
 int se3mpc_rotor_positions_device(int nstates, double wing_len, const double *X, double *pos, void *stream)
 {
     if (nstates < 0 || !X || !pos) return fail(SE3MPC_ERR_INVALID, "invalid argument");
@@ -1103,7 +1152,6 @@ int se3mpc_rotor_positions_host(int nstates, double wing_len, const double *X, d
     if (nstates < 0 || !X || !pos) return fail(SE3MPC_ERR_INVALID, "invalid argument");
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (nstates == 0) return SE3MPC_OK;
-    std::lock_guard<std::mutex> lk(g_host_mu);
     HOST_CTX();
     int rc;
     if ((rc = g_in.ensure(pad((size_t)nstates * 13 * 8))) != SE3MPC_OK) return rc;
@@ -1124,7 +1172,6 @@ int se3mpc_gate_frame_host(int B, const double *gate, const double *velo, const 
     if (B < 0 || !gate || !velo || !w || !t || !state || !final_point || !inputs18) return fail(SE3MPC_ERR_INVALID, "invalid argument");
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0) return SE3MPC_OK;
-    std::lock_guard<std::mutex> lk(g_host_mu);
     HOST_CTX();
     int rc;
     if ((rc = g_in.ensure(pad((size_t)B * 12 * 8) + 2 * pad((size_t)B * 3 * 8) + 2 * pad((size_t)B * 8) + pad((size_t)B * 13 * 8))) != SE3MPC_OK) return rc;
@@ -1153,7 +1200,6 @@ int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps,
     if (!params_ok(p) || B < 0 || !(dt > 0) || nsteps < 0 || !u || !state) return fail(SE3MPC_ERR_INVALID, "invalid argument");
     if (!have_device()) return fail(SE3MPC_ERR_NO_DEVICE, "no CUDA device");
     if (B == 0 || nsteps == 0) return SE3MPC_OK;
-    std::lock_guard<std::mutex> lk(g_host_mu);
     HOST_CTX();
     int rc;
     if ((rc = g_in.ensure(pad((size_t)B * 4 * 8))) != SE3MPC_OK) return rc;
@@ -1171,16 +1217,17 @@ int se3mpc_plant_step_host(const se3mpc_params *p, int B, double dt, int nsteps,
 
 void se3mpc_host_release(void)
 {
-    std::lock_guard<std::mutex> lk(g_host_mu);
     int cur = 0, n = 0;
     if (cudaGetDevice(&cur) != cudaSuccess || cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
-    for (int d = 0; d < n && d < MAX_DEVICES; d++) {
-        HostCtx &h = g_host[d];
-        if (!h.in.p && !h.out.p && !h.ws.p && !h.stream) continue;
-        cudaSetDevice(d);
-        h.in.release(); h.out.release(); h.ws.release();
-        if (h.stream) { cudaStreamDestroy(h.stream); h.stream = nullptr; }
-    }
+    for (int d = 0; d < n && d < MAX_DEVICES; d++)
+        for (int l = 0; l < HOST_LANES; l++) {
+            HostCtx &h = g_host[d][l];
+            std::lock_guard<std::mutex> lk(h.mu);
+            if (!h.in.p && !h.out.p && !h.ws.p && !h.stream) continue;
+            cudaSetDevice(d);
+            h.in.release(); h.out.release(); h.ws.release();
+            if (h.stream) { cudaStreamDestroy(h.stream); h.stream = nullptr; }
+        }
     cudaSetDevice(cur);
 }
 

@@ -35,16 +35,24 @@ def gather_to_rank0(local: torch.Tensor, sizes, dst: int = 0) -> Optional[torch.
 
 
 def sharded_call(fn: Callable[..., Dict[str, torch.Tensor]], inputs: Dict[str, np.ndarray], device=None,
-                 keys=None) -> Optional[Dict[str, torch.Tensor]]:
-    """Run `fn(**shard)` on this rank's contiguous shard of `inputs` (arrays with a leading problem dimension, identical
-    on every rank) and gather the outputs named in `keys` to rank 0 in problem order.  With one process this is fn(**inputs)."""
+                 keys=None, n_total: Optional[int] = None) -> Optional[Dict[str, torch.Tensor]]:
+    """Run `fn(**shard)` on this rank's contiguous shard of the problems and gather the outputs named in `keys` to rank 0 in problem
+    order.  With one process this is fn(**inputs).
+
+    inputs: arrays with a leading problem dimension -- either the FULL batch, identical on every rank (n_total=None: this rank's
+    slice [lo, hi) = shard_range(n, rank, world) is taken here), or, with n_total given, ALREADY this rank's shard of an n_total-problem
+    batch (each rank generated only its own part, e.g. from (seed, index); its length must equal the shard_range size)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    n = next(iter(inputs.values())).shape[0]
+    first = next(iter(inputs.values()))
+    n = int(n_total) if n_total is not None else first.shape[0]
     lo, hi = shard_range(n, rank, world)
+    if n_total is not None and first.shape[0] != hi - lo:
+        raise ValueError(f"pre-sharded input has {first.shape[0]} problems, rank {rank} of {world} owns {hi - lo} of {n}")
     shard = {}
     for k, v in inputs.items():
-        t = torch.as_tensor(np.ascontiguousarray(v[lo:hi]))
+        part = v if n_total is not None else v[lo:hi]
+        t = part if isinstance(part, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(part))
         shard[k] = t.to(device) if device is not None else t
     out = fn(**shard)
     sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]

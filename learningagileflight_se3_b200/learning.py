@@ -23,6 +23,33 @@ from . import ops
 from ._lib import Params, default_params
 
 
+def dnn_from_arrays(arrays, device=None) -> Callable:
+    """Re-assemble a quad_nn.network (quad_nn.py:100-125: Linear-ReLU-Linear-ReLU-Linear, fp32) from plain arrays
+    {l1_weight, l1_bias, l2_weight, l2_bias, l3_weight, l3_bias} (e.g. tests/golden/nn3_1_weights.npz, the reference's shipped DNN-2)
+    as a batched callable: x[B,D_in] (any float dtype / device) -> [B,D_out] float64.  Like the reference's forward it computes in
+    float32 (`torch.tensor(input, dtype=torch.float)`, quad_nn.py:118)."""
+    layers = []
+    for i in (1, 2, 3):
+        W = torch.as_tensor(np.asarray(arrays[f"l{i}_weight"]), dtype=torch.float32)
+        lin = torch.nn.Linear(W.shape[1], W.shape[0])
+        with torch.no_grad():
+            lin.weight.copy_(W)
+            lin.bias.copy_(torch.as_tensor(np.asarray(arrays[f"l{i}_bias"]), dtype=torch.float32))
+        layers += [lin] + ([torch.nn.ReLU()] if i < 3 else [])
+    net = torch.nn.Sequential(*layers)
+    if device is not None:
+        net = net.to(device)
+    net.eval()
+    for q in net.parameters():          # an inference copy of shipped weights (train your own torch module instead)
+        q.requires_grad_(False)
+
+    def model(x):
+        x = torch.as_tensor(x)
+        return net(x.to(device=next(net.parameters()).device, dtype=torch.float32)).to(torch.float64)
+    model.net = net
+    return model
+
+
 def scenario_from_nn_inputs(inputs):
     """inputs[B,9] = nn_sample rows [r0(3), goal(3), yaw, width, pitch] -> dict of numpy arrays x0[B,13], goal[B,3], gate[B,12].
     deep_learning.py:24-30: gate corners (+-w/2, 0, +-1) rotated about y by the pitch (gate.rotate_y_out), x0 = [r0, 0, q(yaw about z), 0]."""

@@ -292,6 +292,25 @@ def plant_step(state, u, dt=0.01, nsteps=1, params: Optional[Params] = None):
     return x
 
 
+def episode_advance(state, gate, u, velo, w, dt=0.01, nsteps=10, noise=None, params: Optional[Params] = None):
+    """One MPC tick between two re-solves (main.py:108 + gate.move): nsteps x {plant Euler step, gate rotation + translation} in ONE
+    launch.  state[B,13] and gate[B,12] are updated IN PLACE (and returned); noise[nsteps,B,3] optional velocity noise."""
+    _require_cuda(state, gate, u, velo, w, noise)
+    p = params or default_params()
+    B, dev = state.shape[0], state.device
+    if not (state.is_contiguous() and gate.is_contiguous() and state.shape == (B, 13) and gate.shape == (B, 12)):
+        raise Se3MpcError("episode_advance updates state[B,13] / gate[B,12] in place: pass contiguous tensors of that shape")
+    u, velo, w = _c(u, (B, 4)), _c(velo, (B, 3)), _c(w, (B,))
+    noise = _c(noise, (int(nsteps), B, 3))
+    if B == 0:
+        return state, gate
+    with torch.cuda.device(dev):
+        rc = _lib.lib().se3mpc_episode_advance_device(C.byref(p), B, float(dt), int(nsteps), _ptr(u), _ptr(state), _ptr(gate), _ptr(velo),
+                                                      _ptr(w), _ptr(noise), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "se3mpc_episode_advance_device")
+    return state, gate
+
+
 def gate_frame_host(gate, velo, w, t, state, final_point, want_gate=False):
     """Host-buffer variant of gate_frame (numpy in, numpy out)."""
     state = _np(state, (-1, 13))

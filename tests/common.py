@@ -15,6 +15,18 @@ def make_gate(width, pitch):
     return out.reshape(12)
 
 
+def make_gates(width, pitch):
+    """make_gate for arrays width[B], pitch[B] -> [B,12] (same arithmetic, vectorised: the 1M-problem sweep of bench.py needs it)."""
+    width, pitch = np.asarray(width, dtype=float), np.asarray(pitch, dtype=float)
+    gx = np.stack([-width / 2, width / 2, width / 2, -width / 2], 1)
+    gz = np.tile(np.array([1.0, 1.0, -1.0, -1.0]), (width.shape[0], 1))
+    c, s = np.cos(pitch)[:, None], np.sin(pitch)[:, None]
+    out = np.zeros((width.shape[0], 4, 3))
+    out[:, :, 0] = c * gx - s * gz
+    out[:, :, 2] = s * gx + c * gz
+    return out.reshape(-1, 12)
+
+
 def sample_scenarios(B, seed, noise=0.2):
     rng = np.random.default_rng(seed)
     r0 = rng.uniform(-5, 5, (B, 3)) + np.array([0, -9, 0])
@@ -31,7 +43,7 @@ def sample_scenarios(B, seed, noise=0.2):
     x0[:, 0:3] = r0
     x0[:, 6] = np.cos(yaw / 2)
     x0[:, 9] = np.sin(yaw / 2)
-    gate = np.stack([make_gate(w, p) for w, p in zip(width, pitch)])
+    gate = make_gates(width, pitch)
     tra_pos = rng.normal(0, noise, (B, 3))
     tra_ang = rng.normal(0, noise, (B, 3))
     t = np.clip(np.round(np.linalg.norm(r0, axis=1) / 4, 1), 2, 4)

@@ -87,5 +87,7 @@ def test_rd2quat(oracle, emu):
 
 
 def test_smem_and_slot_budget(emu):
-    # 4 warps/CTA x 3 CTAs/SM (csrc/se3mpc.cu launch configuration; 4 CTAs/SM must fit too) within the 227 KB of an SM
-    assert emu.lib().se3emu_smem_bytes() * 16 + 4 * 2304 <= 227 * 1024
+    # 4 warps/CTA x 3 CTAs/SM (csrc/se3mpc.cu launch configuration: 2 CTAs/SM for launches up to ~9k problems, 3 above) within the
+    # 227 KB of an SM, counting the lane table and the 1 KB the system reserves per CTA.  (16 warps/SM were measured in round 2: no
+    # faster than 8 -- the L1/shared-memory data pipe is the shared resource -- so the budget no longer has to admit a 4th CTA.)
+    assert emu.lib().se3emu_smem_bytes() * 12 + 3 * 2304 <= 227 * 1024

@@ -202,3 +202,59 @@ def test_quadrotor_shim_plant_and_rotor_positions_run_on_the_gpu(oracle):
     p = oracle.default_params()
     assert np.abs(uav.get_quadrotor_position(1.5, X) - oracle.rotor_positions(p, X)).max() <= 1e-13
     assert ops.rotor_positions_host(np.zeros((0, 13)), 1.5).shape == (0, 15)
+
+
+def test_episode_advance_is_the_fused_form_of_plant_step_and_gate_move():
+    """ONE launch for the 10 sub-steps between two re-solves == 10 x (plant_step ; gate_frame(t = dt) -> predicted corners), bit for bit,
+    with and without velocity noise; ragged batch."""
+    import torch
+    from learningagileflight_se3_b200 import ops
+    dev = torch.device("cuda", 0)
+    d = np.load(GOLD)
+    rng = np.random.default_rng(9)
+    B, n = 37, 10
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)  # noqa: E731
+    x = rng.normal(0, 1, (B, 13)); u = rng.uniform(0, 2.44, (B, 4))
+    gates = np.resize(d["gates"], (B, 12)) + rng.normal(0, 0.1, (B, 12))
+    velo = rng.normal(0, 1, (B, 3)); w = rng.uniform(-1, 1, B); fin = rng.normal(0, 1, (B, 3))
+    for noise in (None, rng.normal(0, 0.3, (n, B, 3))):
+        xs, gs = tt(x), tt(gates)
+        for j in range(n):
+            xs = ops.plant_step(xs, tt(u), 0.01, 1)
+            v = tt(velo) if noise is None else tt(velo + noise[j])
+            _, gs = ops.gate_frame(gs, v, tt(w), torch.full((B,), 0.01, dtype=torch.float64, device=dev), xs, tt(fin), want_gate=True)
+        xf, gf = tt(x), tt(gates)
+        ops.episode_advance(xf, gf, tt(u), tt(velo), tt(w), 0.01, n, noise=None if noise is None else tt(noise))
+        assert torch.equal(xf, xs) and torch.equal(gf, gs)
+
+
+def test_closed_loop_is_sync_free_and_invariant_to_stream_groups():
+    """run_episodes with 1 and 3 stream groups (and the fixed-point with / without host checks): identical controls, states, status."""
+    import torch
+    from learningagileflight_se3_b200 import quad_moving
+    d = np.load(GOLD)
+    dev = torch.device("cuda", 0)
+    B, ticks = 10, 2
+    rng = np.random.default_rng(12)
+    state0 = np.zeros((B, 13)); state0[:, 0:3] = rng.uniform(-2, 2, (B, 3)) + np.array([0, -6, 0]); state0[:, 6] = 1.0
+    final = rng.uniform(-1, 1, (B, 3)) + np.array([0, 6, 0])
+    gates = np.resize(d["gates"], (B, 12)).reshape(B, 4, 3)
+    gates = (gates - gates.mean(1, keepdims=True)).reshape(B, 12)
+    velo = np.tile(np.array([0.3, 0.1, 0.1]), (B, 1)); w = 0.5
+    net_t = _torch_net(d, dev)
+
+    def model_t(x):
+        y = net_t(x)
+        return torch.cat([0.1 * torch.tanh(y[:, 0:6]), y[:, 6:7]], 1)
+    tt = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)  # noqa: E731
+    noise = tt(rng.normal(0, 0.05, (ticks * 10, B, 3)))
+    t_a, it_a = quad_moving.traversal_time(model_t, tt(state0), tt(final), tt(gates), tt(velo), w)                    # host check every iteration
+    t_b, it_b, act = quad_moving.traversal_time(model_t, tt(state0), tt(final), tt(gates), tt(velo), w, max_iter=24, check_every=0, return_active=True)
+    assert torch.equal(t_a, t_b) and torch.equal(it_a, it_b) and int(act.sum()) == 0 and int(it_a.max()) < 24
+    r1 = quad_moving.run_episodes(model_t, tt(state0), tt(final), tt(gates), tt(velo), w, n_ticks=ticks, gate_noise=noise, record=True)
+    r3 = quad_moving.run_episodes(model_t, tt(state0), tt(final), tt(gates), tt(velo), w, n_ticks=ticks, gate_noise=noise, record=True, groups=3)
+    torch.cuda.synchronize()
+    assert int(r1["tt_unconverged"].sum()) == 0
+    for k in ("state", "gate", "controls", "status", "t_tra", "iters", "states"):
+        assert r1[k].shape == r3[k].shape and torch.equal(r1[k], r3[k]), k
+    assert r1["controls"].shape == (B, ticks, 4) and (r1["status"] <= 1).all()

@@ -86,3 +86,14 @@ def test_model_batch_helper_with_the_reference_network_and_row_models():
         with torch.no_grad():
             want = torch.stack([m(x[j]) for j in range(9)])
         assert float((_model_batch(m, x).detach() - want).abs().max()) <= 1e-6
+
+
+def test_shipped_dnn2_fixture_reproduces_the_reference_module():
+    """tests/golden/nn3_1_weights.npz (exported from gym_pybullet_drone/nn3_1.pth by make_golden_nn3.py) re-assembled by
+    learning.dnn_from_arrays gives the outputs the reference's own forward produced, batched."""
+    from learningagileflight_se3_b200.learning import dnn_from_arrays
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "nn3_1_weights.npz"))
+    model = dnn_from_arrays(d)
+    with torch.no_grad():
+        y = model(d["probe_in"]).numpy()
+    assert y.shape == (16, 7) and np.abs(y - d["probe_out"]).max() <= 2e-5 * max(1.0, np.abs(d["probe_out"]).max())
