@@ -268,6 +268,8 @@ struct RArgs {
     const double *X, *gate, *goal;
     double *reward, *collision, *path;
     int32_t *co;
+    int32_t *tcross;           // scratch [B]: the first plane crossing of the four rotor tips, 8 bits each (0xFF: none)
+    double *pathsum;           // scratch [B]
 };
 
 // Stand-alone reward: one THREAD per trajectory; a warp streams its 32 trajectories through shared memory in chunks of RW_CH
@@ -378,20 +380,50 @@ __global__ void __launch_bounds__(RW_WARPS * 32, RW_CTAS) se3mpc_reward_kernel(c
             }
             __syncwarp();           // every lane is done with this buffer before the issue of the next iteration refills it
         }
-        double col;
-        int co;
-        const double *Xp = a.X + (size_t)pbc * nst * 13;
-        const double r = acc.finish(gate, [&](int t, double *x) {
-#pragma unroll
-            for (int i = 0; i < 13; i++) x[i] = __ldg(Xp + t * 13 + i);
-        }, &col, &co);
+        // the streaming pass ends here: the (rare, branchy, register-hungry) scoring of the four crossings is a second, small kernel
         if (live) {
-            a.reward[pb] = r;
-            if (a.collision) a.collision[pb] = col;
-            if (a.path) a.path[pb] = acc.path;
-            if (a.co) a.co[pb] = co;
+            unsigned packed = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) packed |= (unsigned)(acc.tcross[r] & 0xFF) << (8 * r);
+            a.tcross[pb] = (int32_t)packed;
+            a.pathsum[pb] = acc.path;
         }
     }
+}
+
+// Second pass of the stand-alone reward: one thread per trajectory builds the gate's wedge normals once and scores the recorded
+// crossings of the four rotor tips from the two states around each (2 x 104 B gathered per rotor), then assembles
+// reward = 1000 collision - 0.5 path + 100 (quad_policy.py:90) with the rotor scores summed in the reference's order.
+__global__ void __launch_bounds__(128) se3mpc_reward_score_kernel(const __grid_constant__ RArgs a)
+{
+    const int pb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pb >= a.B) return;
+    const int nst = a.par.N + 1;
+    double gate[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) gate[i] = __ldg(a.gate + (size_t)pb * 12 + i);
+    se3::Gate G;
+    se3::gate_setup(gate, G);
+    const unsigned packed = (unsigned)a.tcross[pb];
+    const double arm = a.par.wing_len * 0.5 / sqrt(2.0);
+    const double *Xp = a.X + (size_t)pb * nst * 13;
+    double col = 0.0;
+    int cosum = 0;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int tb = (int)((packed >> (8 * r)) & 0xFF), t = (tb == 0xFF) ? -1 : tb;
+        int co = 0;
+        col += se3::rotor_crossing_score(G, arm, r, t, [&](int tt, double *x) {
+#pragma unroll
+            for (int i = 0; i < 13; i++) x[i] = __ldg(Xp + tt * 13 + i);
+        }, &co);
+        cosum += co;
+    }
+    const double path = a.pathsum[pb];
+    a.reward[pb] = 1000 * col - 0.5 * path + 100;          // quad_policy.py:90
+    if (a.collision) a.collision[pb] = col;
+    if (a.path) a.path[pb] = path;
+    if (a.co) a.co[pb] = cosum;
 }
 
 __global__ void __launch_bounds__(256) se3mpc_collis_kernel(int B, int horizon, const double *V, const double *gate, double *score,
@@ -783,13 +815,23 @@ int se3mpc_reward_device(const se3mpc_params *p, int B, const double *X, const d
     if (B == 0) return SE3MPC_OK;
     RArgs a;
     a.par = *p; a.B = B; a.X = X; a.gate = gate; a.goal = goal; a.reward = reward; a.collision = collision; a.path = path; a.co = co;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // 12 bytes of scratch per trajectory between the two passes, stream-ordered (freed when the second pass is done)
+    void *scratch = nullptr;
+    const size_t off_path = ((size_t)B * sizeof(int32_t) + 255) / 256 * 256;
+    CK(cudaMallocAsync(&scratch, off_path + (size_t)B * sizeof(double), st));
+    a.tcross = static_cast<int32_t *>(scratch);
+    a.pathsum = reinterpret_cast<double *>(static_cast<unsigned char *>(scratch) + off_path);
     int grid = ((B + 31) / 32 + RW_WARPS - 1) / RW_WARPS;       // one thread per trajectory, RW_WARPS warps per CTA
     const int cap = num_sms() * RW_CTAS * 2;
     if (grid > cap) grid = cap;
-    { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) return rc_attr; }
-    se3mpc_reward_kernel<<<grid, RW_WARPS * 32, RW_SMEM, static_cast<cudaStream_t>(stream)>>>(a);
-    g_launches++;
-    CK(cudaGetLastError());
+    { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) { cudaFreeAsync(scratch, st); return rc_attr; } }
+    se3mpc_reward_kernel<<<grid, RW_WARPS * 32, RW_SMEM, st>>>(a);
+    se3mpc_reward_score_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
+    g_launches += 2;
+    const cudaError_t e_launch = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e_launch != cudaSuccess) return fail(SE3MPC_ERR_CUDA, "se3mpc_reward launch", e_launch);
     return SE3MPC_OK;
 }
 

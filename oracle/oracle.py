@@ -227,7 +227,7 @@ def _sol_dict(p, sol: Solution):
         "x_raw": np.array(sol.XRAW[: (N + 1) * 13]).reshape(N + 1, 13), "u_raw": np.array(sol.URAW[: N * 4]).reshape(N, 4),
         "zL": np.array(sol.ZL[: N * 17 + 13]), "zU": np.array(sol.ZU[: N * 17 + 13]),
         "cost": float(sol.cost), "status": int(sol.status), "iters": int(sol.iters), "nfact": int(sol.nfact),
-        "nls": int(sol.nls), "nsoc": int(sol.nsoc), "kkt_error": float(sol.kkt_error), "mu": float(sol.mu),
+        "nls": int(sol.nls), "nsoc": int(sol.nsoc), "nresto": int(sol.nresto), "kkt_error": float(sol.kkt_error), "mu": float(sol.mu),
         "obj_scale": float(sol.obj_scale), "dual_inf": float(sol.dual_inf), "constr_viol": float(sol.constr_viol),
         "compl_inf": float(sol.compl_inf),
     }

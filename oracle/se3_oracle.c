@@ -821,6 +821,38 @@ static double kkt_error(ipm_t *s, double mu, double *dual_inf, double *cviol, do
     return fmax(dinf / sd, fmax(cv, cmp / sc));
 }
 
+/* IPOPT's primal-dual system error (IpIpoptCalculatedQuantities::curr_primal_dual_system_error): averaged 1-norms of the dual
+ * infeasibility, the constraint violation and the mu-complementarity at the current iterate (eval_point must be current). */
+static double pd_system_error(ipm_t *s, double mu)
+{
+    const int N = s->N;
+    double dual = 0, prim = 0, cmp = 0;
+    for (int k = 0; k < N; k++) {
+        for (int j = 0; j < NU; j++) {
+            double v = s->sf * s->ogu[k][j] - s->zLu[k][j] + s->zUu[k][j];
+            for (int l = 0; l < NX; l++) v += s->st[k].B[l][j] * s->lam[k][l];
+            dual += fabs(v);
+            double sl = s->u[k][j] - s->uL, su = s->uU - s->u[k][j];
+            cmp += fabs(sl * s->zLu[k][j] - mu) + fabs(su * s->zUu[k][j] - mu);
+        }
+        for (int i = 0; i < NX; i++) prim += fabs(s->c[k][i]);
+    }
+    for (int k = 1; k <= N; k++) {
+        for (int i = 0; i < NX; i++) {
+            double v = s->sf * s->ogx[k][i] - s->lam[k - 1][i];
+            if (k < N)
+                for (int l = 0; l < NX; l++) v += s->st[k].A[l][i] * s->lam[k][l];
+            if (i >= 10) v += -s->zLw[k][i - 10] + s->zUw[k][i - 10];
+            dual += fabs(v);
+        }
+        for (int j = 0; j < 3; j++) {
+            double sl = s->x[k][10 + j] - s->wL, su = s->wU - s->x[k][10 + j];
+            cmp += fabs(sl * s->zLw[k][j] - mu) + fabs(su * s->zUw[k][j] - mu);
+        }
+    }
+    return dual / (double)((NX + NU) * N) + prim / (double)(NX * N) + cmp / (double)(2 * (NU + 3) * N);
+}
+
 static void eval_point(ipm_t *s)
 {   /* constraints, objective gradient and dynamics Jacobians at the current iterate */
     nlp_constraints(s, s->x, s->u, s->c);
@@ -917,6 +949,8 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
     double delta_last = 0.0;
     int acc_count = 0, status = 2, iter = 0;
     int nls = 0, nsoc = 0;
+    int in_soft_resto = 0, soft_resto_counter = 0, nsoft = 0;
+    int consec_short = 0, max_consec_short = 0;       /* IPOPT's soft restoration phase (IpBacktrackingLineSearch.cpp) */
     double fcur = nlp_objective(s, s->x, s->u, NULL, NULL);
 
     for (iter = 0;; iter++) {
@@ -985,7 +1019,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
         double (*ddx)[NX] = s->dx, (*ddu)[NU] = s->du;
         double alpha_test = alpha;
         double ftrial = 0;
-        while (!accepted) {
+        while (!accepted && !in_soft_resto) {
             nls++;
             for (int k = 0; k <= N; k++)
                 for (int i = 0; i < NX; i++) s->xt[k][i] = s->x[k][i] + alpha * s->dx[k][i];
@@ -1015,6 +1049,9 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
                 ok_ = a_;                                                                                    \
             } while (0)
             ACCEPTABLE(theta_t, phi_t, accepted);
+            if (getenv("SE3O_VERBOSE4"))
+                fprintf(stderr, "      trial alpha=%.3e theta_t=%.6e (theta_k %.6e) phi_t=%.8e (phi_k %.8e) gphid=%.3e alpha_min=%.3e acc=%d\n", alpha, theta_t,
+                        theta_k, phi_t, phi_k, gphid, alpha_min, accepted);
             if (accepted) break;
             /* second-order correction (first trial only, constraint violation not reduced) */
             if (first && p->max_soc > 0 && theta_t >= theta_k) {
@@ -1066,10 +1103,73 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
             if (alpha < alpha_min) break;
         }
         (void)ddx; (void)ddu;
-        if (!accepted) { status = 3; break; }
+        if (!accepted && (p->flags & SE3O_FLAG_SOFT_RESTO)) {
+            /* The backtracking line search ran below alpha_min (or the soft restoration phase is already active): IPOPT tries a
+             * "soft restoration" step before it calls the restoration phase proper (TrySoftRestoStep): the ORIGINAL direction with
+             * ONE step size for primal and dual variables, alpha = min(alpha_primal_max, alpha_dual_max) of the fraction-to-the-
+             * boundary rule; accepted if the point is acceptable to the original filter criterion (then the phase ends) or if it
+             * reduces the primal-dual system error by soft_resto_pderror_reduction_factor = 0.9999; at most max_soft_resto_iters =
+             * 10 consecutive such steps.  The filter is not augmented by soft steps. */
+            int try_it = 1;
+            if (in_soft_resto) { soft_resto_counter++; if (soft_resto_counter > 10) try_it = 0; }
+            if (try_it) {
+                compute_dz(s, mu, s->dx, s->du);                     /* (a rejected SOC may have left dz of its own direction) */
+                const double a_s = fmin(frac_to_bound_primal(s, s->dx, s->du, tau), frac_to_bound_dual(s, tau));
+                const double pd_cur = pd_system_error(s, mu);
+                ipm_t *bk = (ipm_t *)malloc(sizeof(ipm_t));
+                memcpy(bk, s, sizeof(ipm_t));
+                for (int k = 1; k <= N; k++)
+                    for (int i = 0; i < NX; i++) s->x[k][i] += a_s * s->dx[k][i];
+                for (int k = 0; k < N; k++) {
+                    for (int j = 0; j < NU; j++) {
+                        s->u[k][j] += a_s * s->du[k][j];
+                        s->zLu[k][j] += a_s * s->dzLu[k][j]; s->zUu[k][j] += a_s * s->dzUu[k][j];
+                    }
+                    for (int i = 0; i < NX; i++) s->lam[k][i] += a_s * (s->lamp[k][i] - s->lam[k][i]);
+                }
+                for (int k = 1; k <= N; k++)
+                    for (int j = 0; j < 3; j++) { s->zLw[k][j] += a_s * s->dzLw[k][j]; s->zUw[k][j] += a_s * s->dzUw[k][j]; }
+                eval_point(s);
+                nls++;
+                const double theta_t = theta_of(s, s->c);
+                const double f_t = nlp_objective(s, s->x, s->u, NULL, NULL);
+                const double phi_t = barrier_obj(s, s->x, s->u, mu, f_t);
+                int orig_ok = 0;
+                alpha_test = 0.0;                                     /* CheckAcceptabilityOfTrialPoint(0.) */
+                ACCEPTABLE(theta_t, phi_t, orig_ok);
+                int soft_ok = orig_ok;
+                if (!soft_ok && isfinite(theta_t) && isfinite(phi_t)) {
+                    const double pd_t = pd_system_error(s, mu);
+                    soft_ok = isfinite(pd_t) && pd_t <= 0.9999 * pd_cur;
+                }
+                if (soft_ok) {
+                    /* kappa_sigma safeguard of the bound multipliers, as after every accepted step */
+                    const double ks = 1e10;
+#define ZFIX(z, slack) do { double sl_ = (slack); (z) = fmax(fmin((z), ks * mu / sl_), mu / (ks * sl_)); } while (0)
+                    for (int k = 0; k < N; k++)
+                        for (int j = 0; j < NU; j++) { ZFIX(s->zLu[k][j], s->u[k][j] - s->uL); ZFIX(s->zUu[k][j], s->uU - s->u[k][j]); }
+                    for (int k = 1; k <= N; k++)
+                        for (int j = 0; j < 3; j++) { ZFIX(s->zLw[k][j], s->x[k][10 + j] - s->wL); ZFIX(s->zUw[k][j], s->wU - s->x[k][10 + j]); }
+#undef ZFIX
+                    if (orig_ok) { in_soft_resto = 0; soft_resto_counter = 0; }
+                    else if (!in_soft_resto) { in_soft_resto = 1; soft_resto_counter = 0; }
+                    fcur = f_t;
+                    nsoft++;
+                    free(bk);
+                    if (getenv("SE3O_VERBOSE3")) fprintf(stderr, "   soft restoration step alpha=%.3e orig_ok=%d\n", a_s, orig_ok);
+                    continue;
+                }
+                const int nfact_keep = s->nfact;
+                memcpy(s, bk, sizeof(ipm_t));
+                s->nfact = nfact_keep;
+                free(bk);
+            }
+        }
+        if (!accepted) { status = 3; break; }          /* IPOPT would now enter the feasibility restoration phase (not implemented) */
         if (getenv("SE3O_VERBOSE3"))
             fprintf(stderr, "   ls: alpha_max=%.3e alpha=%.3e alpha_z=%.3e ntrial_total=%d gphid=%.3e theta_k=%.3e theta_t? nfilt=%d\n", alpha_max, alpha, alpha_z, nls, gphid, theta_k, nfilt);
 
+        if (alpha < alpha_max) { consec_short++; if (consec_short > max_consec_short) max_consec_short = consec_short; } else consec_short = 0;
         /* filter augmentation (uses the original alpha_test / direction) */
         {
             int ftype = (gphid < 0) && (alpha_test * pow(-gphid, s_phi) > pow(theta_k, s_theta));
@@ -1125,7 +1225,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
         for (int j = 0; j < 3 && k >= 1; j++) { sol->ZL[k * 17 + 10 + j] = s->zLw[k][j]; sol->ZU[k * 17 + 10 + j] = s->zUw[k][j]; }
     for (int k = 0; k < N; k++)
         for (int j = 0; j < NU; j++) { sol->ZL[k * 17 + NX + j] = s->zLu[k][j]; sol->ZU[k * 17 + NX + j] = s->zUu[k][j]; }
-    sol->status = status; sol->iters = iter; sol->nfact = s->nfact; sol->nls = nls; sol->nsoc = nsoc;
+    sol->status = status; sol->iters = iter; sol->nfact = s->nfact; sol->nls = nls; sol->nsoc = nsoc; sol->nresto = getenv("SE3O_STAT") ? max_consec_short : nsoft;
     sol->mu = mu;
     free(s);
     return status;
