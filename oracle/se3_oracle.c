@@ -867,6 +867,612 @@ static int all_finite(const double *v, int n)
     return 1;
 }
 
+/* =====================================================================================================================
+ * Feasibility restoration phase -- IPOPT's MinC_1NrmRestorationPhase (Waechter & Biegler 2006, section 3.3; IPOPT 3.12
+ * IpRestoMinC_1Nrm.cpp, IpRestoIpoptNLP.cpp, IpRestoIterateInitializer.cpp, IpRestoConvCheck.cpp), entered when the filter
+ * line search of the regular algorithm runs below alpha_min.  With y = (x_1..x_N, u_0..u_{N-1}) and the reference point y_R =
+ * the current iterate, it solves
+ *      min  rho sum(n + p) + eta(mu)/2 ||D_R (y - y_R)||^2     s.t.  c(y) - p + n = 0,  n, p >= 0,  y_L <= y <= y_U
+ * (rho = 1000, eta(mu) = sqrt(mu), D_R = diag(1 / max(1, |y_R|))) by the SAME interior-point algorithm (monotone mu starting at
+ * max(mu, ||c||_inf), filter line search with second-order correction, inertia correction) until the y part is acceptable to the
+ * ORIGINAL filter and has reduced the ORIGINAL constraint violation to kappa_resto = 0.9 of its value at entry.  The slack
+ * variables are eliminated from the Newton system analytically (IpAugRestoSystemSolver): what is left is the regular KKT system
+ * with a negative diagonal block,  [H  J^T; J  -D],  D = n/z_n + p/z_p, i.e. a Riccati recursion with "soft" dynamics:
+ * (P', p') of a stage enter through  P~ = P' - P' D^1/2 T^-1 D^1/2 P',  T = I + D^1/2 P' D^1/2  (13 x 13 Cholesky per stage).
+ * ===================================================================================================================== */
+#define RESTO_RHO 1000.0
+typedef struct {
+    double n[NMAX][NX], p[NMAX][NX], zn[NMAX][NX], zp[NMAX][NX], lam[NMAX][NX];
+    double dn[NMAX][NX], dp[NMAX][NX], dzn[NMAX][NX], dzp[NMAX][NX], lamp[NMAX][NX];
+    double xR[NMAX + 1][NX], uR[NMAX][NU], dRx[NMAX + 1][NX], dRu[NMAX][NU];
+    double D[NMAX][NX];                                   /* n/z_n + p/z_p */
+    double LT[NMAX][NX][NX], Pn[NMAX + 1][NX][NX], pn[NMAX + 1][NX];        /* chol(T_k), P_{k+1}, p_{k+1} as seen by stage k */
+    double gx[NMAX + 1][NX], gu[NMAX][NU], chat[NMAX][NX], h[NMAX][NX];
+    double nt[NMAX][NX], pt[NMAX][NX];                    /* trial slacks */
+} resto_t;
+
+static int chol13(double T[NX][NX], double L[NX][NX])
+{
+    memset(L, 0, sizeof(double) * NX * NX);
+    for (int j = 0; j < NX; j++) {
+        double d = T[j][j];
+        for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+        if (!(d > 4.0 * DBL_EPSILON * fabs(T[j][j])) || !(d > 0)) return 0;
+        L[j][j] = sqrt(d);
+        for (int i = j + 1; i < NX; i++) {
+            double v = T[i][j];
+            for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+            L[i][j] = v / L[j][j];
+        }
+    }
+    return 1;
+}
+static void chol13_solve(double L[NX][NX], const double *b, double *x)
+{
+    double y[NX];
+    for (int i = 0; i < NX; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= L[i][k] * y[k]; y[i] = v / L[i][i]; }
+    for (int i = NX - 1; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < NX; k++) v -= L[k][i] * x[k]; x[i] = v / L[i][i]; }
+}
+
+/* Riccati sweep of the restoration system [H J^T; J -D][d; lam+] = -[g; chat].  H = eta D_R^2 + sum lam hess(c) + Sigma + delta_w I
+ * (ident: H = I).  Returns 1 iff every T_k and H_uu,k is positive definite <=> inertia (n, m, 0). */
+static int riccati_resto(ipm_t *s, resto_t *R, int ident, int do_factor, double delta_w, double eta,
+                         double (*dx)[NX], double (*du)[NU], double (*lamp)[NX])
+{
+    const int N = s->N;
+    if (do_factor) {
+        memset(R->Pn[N], 0, sizeof(R->Pn[N]));
+        for (int i = 0; i < NX; i++) {
+            double q = ident ? 1.0 : eta * R->dRx[N][i] * R->dRx[N][i] + delta_w;
+            if (!ident && i >= 10) {
+                double sl = s->x[N][i] - s->wL, su = s->wU - s->x[N][i];
+                q += s->zLw[N][i - 10] / sl + s->zUw[N][i - 10] / su;
+            }
+            R->Pn[N][i][i] = q;
+        }
+    }
+    memcpy(R->pn[N], R->gx[N], sizeof(double) * NX);
+    for (int k = N - 1; k >= 0; k--) {
+        stage_t *S = &s->st[k];
+        double (*Pp)[NX] = R->Pn[k + 1];
+        const double *D = R->D[k];
+        double sq[NX];
+        for (int i = 0; i < NX; i++) sq[i] = sqrt(D[i]);
+        if (do_factor) {
+            se3o_dyn_jac(s->p, s->x[k], s->u[k], &S->A[0][0], &S->B[0][0]);
+            double T[NX][NX];
+            for (int i = 0; i < NX; i++)
+                for (int j = 0; j < NX; j++) T[i][j] = sq[i] * Pp[i][j] * sq[j] + (i == j ? 1.0 : 0.0);
+            if (!chol13(T, R->LT[k])) return 0;
+            /* P~ = P' - Y^T Y',  column j of T^-1 D^1/2 P' by two triangular solves */
+            double Pt[NX][NX];
+            for (int j = 0; j < NX; j++) {
+                double b[NX], z[NX];
+                for (int i = 0; i < NX; i++) b[i] = sq[i] * Pp[i][j];
+                chol13_solve(R->LT[k], b, z);
+                for (int i = 0; i < NX; i++) {
+                    double v = Pp[i][j];
+                    for (int l = 0; l < NX; l++) v -= Pp[i][l] * sq[l] * z[l];
+                    Pt[i][j] = v;
+                }
+            }
+            for (int i = 0; i < NX; i++)
+                for (int j = i + 1; j < NX; j++) Pt[i][j] = Pt[j][i] = 0.5 * (Pt[i][j] + Pt[j][i]);
+            double Q[NX][NX], Sx[NX][NU], Rm[NU][NU];
+            memset(Q, 0, sizeof(Q)); memset(Sx, 0, sizeof(Sx)); memset(Rm, 0, sizeof(Rm));
+            if (!ident) {
+                double Hd[17 * 17];
+                se3o_dyn_hess(s->p, s->x[k], s->u[k], R->lam[k], Hd);
+                for (int i = 0; i < NX; i++) {
+                    for (int j = 0; j < NX; j++) Q[i][j] = Hd[i * 17 + j];
+                    for (int j = 0; j < NU; j++) Sx[i][j] = Hd[i * 17 + NX + j];
+                    Q[i][i] += eta * R->dRx[k][i] * R->dRx[k][i] + delta_w;
+                }
+                if (k >= 1)
+                    for (int j = 0; j < 3; j++) {
+                        double sl = s->x[k][10 + j] - s->wL, su = s->wU - s->x[k][10 + j];
+                        Q[10 + j][10 + j] += s->zLw[k][j] / sl + s->zUw[k][j] / su;
+                    }
+                for (int i = 0; i < NU; i++) {
+                    for (int j = 0; j < NU; j++) Rm[i][j] = Hd[(NX + i) * 17 + NX + j];
+                    double sl = s->u[k][i] - s->uL, su = s->uU - s->u[k][i];
+                    Rm[i][i] += eta * R->dRu[k][i] * R->dRu[k][i] + s->zLu[k][i] / sl + s->zUu[k][i] / su + delta_w;
+                }
+            } else {
+                for (int i = 0; i < NX; i++) Q[i][i] = 1.0;
+                for (int i = 0; i < NU; i++) Rm[i][i] = 1.0;
+            }
+            double W[NX][NX], Y[NX][NU], Huu[NU][NU];
+            for (int i = 0; i < NX; i++) {
+                for (int j = 0; j < NX; j++) { double v = 0; for (int l = 0; l < NX; l++) v += Pt[i][l] * S->A[l][j]; W[i][j] = v; }
+                for (int j = 0; j < NU; j++) { double v = 0; for (int l = 0; l < NX; l++) v += Pt[i][l] * S->B[l][j]; Y[i][j] = v; }
+            }
+            for (int a = 0; a < NU; a++) {
+                for (int j = 0; j < NX; j++) { double v = Sx[j][a]; for (int l = 0; l < NX; l++) v += Y[l][a] * S->A[l][j]; S->Hux[a][j] = v; }
+                for (int b = 0; b < NU; b++) { double v = Rm[a][b]; for (int l = 0; l < NX; l++) v += S->B[l][a] * Y[l][b]; Huu[a][b] = v; }
+            }
+            for (int a = 0; a < NU; a++)
+                for (int b = a + 1; b < NU; b++) Huu[a][b] = Huu[b][a] = 0.5 * (Huu[a][b] + Huu[b][a]);
+            s->nfact += (k == N - 1);
+            if (!chol4(Huu, S->L)) return 0;
+            for (int j = 0; j < NX; j++) {
+                double col[NU], b4[NU];
+                for (int a = 0; a < NU; a++) b4[a] = S->Hux[a][j];
+                chol4_solve(S->L, b4, col);
+                for (int a = 0; a < NU; a++) S->K[a][j] = -col[a];
+            }
+            if (k >= 1) {
+                for (int i = 0; i < NX; i++)
+                    for (int j = 0; j < NX; j++) {
+                        double v = Q[i][j];
+                        for (int l = 0; l < NX; l++) v += S->A[l][i] * W[l][j];
+                        for (int a = 0; a < NU; a++) v += S->Hux[a][i] * S->K[a][j];
+                        R->Pn[k][i][j] = v;
+                    }
+                for (int i = 0; i < NX; i++)
+                    for (int j = i + 1; j < NX; j++) R->Pn[k][i][j] = R->Pn[k][j][i] = 0.5 * (R->Pn[k][i][j] + R->Pn[k][j][i]);
+            }
+            memcpy(S->Pxx, Pt, sizeof(Pt));             /* P~ of this stage (vector recursion below) */
+        }
+        /* vector recursion with p~ = p' - P' D^1/2 T^-1 D^1/2 p' */
+        double b[NX], z[NX], pt[NX], tv[NX], hx[NX], hu[NU], kk[NU];
+        for (int i = 0; i < NX; i++) b[i] = sq[i] * R->pn[k + 1][i];
+        chol13_solve(R->LT[k], b, z);
+        for (int i = 0; i < NX; i++) { double v = R->pn[k + 1][i]; for (int l = 0; l < NX; l++) v -= Pp[i][l] * sq[l] * z[l]; pt[i] = v; }
+        for (int i = 0; i < NX; i++) { double v = pt[i]; for (int l = 0; l < NX; l++) v += S->Pxx[i][l] * R->chat[k][l]; tv[i] = v; }
+        for (int i = 0; i < NX; i++) { double v = R->gx[k][i]; for (int l = 0; l < NX; l++) v += S->A[l][i] * tv[l]; hx[i] = v; }
+        for (int a = 0; a < NU; a++) { double v = R->gu[k][a]; for (int l = 0; l < NX; l++) v += S->B[l][a] * tv[l]; hu[a] = v; }
+        chol4_solve(S->L, hu, kk);
+        for (int a = 0; a < NU; a++) S->kff[a] = -kk[a];
+        for (int i = 0; i < NX; i++) { double v = hx[i]; for (int a = 0; a < NU; a++) v += S->Hux[a][i] * S->kff[a]; R->pn[k][i] = v; }
+    }
+    memset(dx[0], 0, sizeof(double) * NX);
+    for (int k = 0; k < N; k++) {
+        stage_t *S = &s->st[k];
+        double (*Pp)[NX] = R->Pn[k + 1];
+        const double *D = R->D[k];
+        for (int a = 0; a < NU; a++) { double v = S->kff[a]; for (int j = 0; j < NX; j++) v += S->K[a][j] * dx[k][j]; du[k][a] = v; }
+        double v13[NX], b[NX], z[NX];
+        for (int i = 0; i < NX; i++) {
+            double v = R->chat[k][i] - D[i] * R->pn[k + 1][i];
+            for (int j = 0; j < NX; j++) v += S->A[i][j] * dx[k][j];
+            for (int a = 0; a < NU; a++) v += S->B[i][a] * du[k][a];
+            v13[i] = v;
+        }
+        /* dx+ = (I + D P')^-1 v = v - D^1/2 T^-1 D^1/2 P' v */
+        for (int i = 0; i < NX; i++) { double t = 0; for (int l = 0; l < NX; l++) t += Pp[i][l] * v13[l]; b[i] = sqrt(D[i]) * t; }
+        chol13_solve(R->LT[k], b, z);
+        for (int i = 0; i < NX; i++) dx[k + 1][i] = v13[i] - sqrt(D[i]) * z[i];
+        for (int i = 0; i < NX; i++) { double v = R->pn[k + 1][i]; for (int j = 0; j < NX; j++) v += Pp[i][j] * dx[k + 1][j]; lamp[k][i] = v; }
+    }
+    return 1;
+}
+
+static double resto_objective(const ipm_t *s, const resto_t *R, double (*x)[NX], double (*u)[NU], double (*n)[NX], double (*p)[NX], double eta)
+{
+    double f = 0, q = 0;
+    for (int k = 0; k < s->N; k++)
+        for (int i = 0; i < NX; i++) f += n[k][i] + p[k][i];
+    for (int k = 1; k <= s->N; k++)
+        for (int i = 0; i < NX; i++) { double d = R->dRx[k][i] * (x[k][i] - R->xR[k][i]); q += d * d; }
+    for (int k = 0; k < s->N; k++)
+        for (int j = 0; j < NU; j++) { double d = R->dRu[k][j] * (u[k][j] - R->uR[k][j]); q += d * d; }
+    return RESTO_RHO * f + 0.5 * eta * q;
+}
+static double resto_barrier(const ipm_t *s, double (*x)[NX], double (*u)[NU], double (*n)[NX], double (*p)[NX], double mu, double f)
+{
+    double b = 0;
+    for (int k = 0; k < s->N; k++)
+        for (int i = 0; i < NX; i++) {
+            if (!(n[k][i] > 0) || !(p[k][i] > 0)) return INFINITY;
+            b += log(n[k][i]) + log(p[k][i]);
+        }
+    ipm_t *ss = (ipm_t *)s;
+    const double sf = ss->sf;
+    ss->sf = 1.0;
+    double v = barrier_obj(s, x, u, mu, f);          /* f - mu sum ln(slacks of y) */
+    ss->sf = sf;
+    return v - mu * b;
+}
+static double resto_theta(const ipm_t *s, double (*c)[NX], double (*n)[NX], double (*p)[NX])
+{
+    double t = 0;
+    for (int k = 0; k < s->N; k++)
+        for (int i = 0; i < NX; i++) t += fabs(c[k][i] - p[k][i] + n[k][i]);
+    return t;
+}
+
+/* scaled optimality error of the restoration problem (same E_mu definition, all multipliers counted) */
+static double resto_kkt_error(ipm_t *s, resto_t *R, double mu, double eta)
+{
+    const int N = s->N;
+    double dinf = 0, cv = 0, cmp = 0, lam1 = 0, z1 = 0;
+#define UPD(v) do { double a_ = fabs(v); if (a_ > dinf) dinf = a_; } while (0)
+#define CMP(sl, z) do { double a_ = fabs((sl) * (z) - mu); if (a_ > cmp) cmp = a_; z1 += fabs(z); } while (0)
+    for (int k = 0; k < N; k++) {
+        for (int j = 0; j < NU; j++) {
+            double v = eta * R->dRu[k][j] * R->dRu[k][j] * (s->u[k][j] - R->uR[k][j]) - s->zLu[k][j] + s->zUu[k][j];
+            for (int l = 0; l < NX; l++) v += s->st[k].B[l][j] * R->lam[k][l];
+            UPD(v);
+            CMP(s->u[k][j] - s->uL, s->zLu[k][j]); CMP(s->uU - s->u[k][j], s->zUu[k][j]);
+        }
+        for (int i = 0; i < NX; i++) {
+            double hv = s->c[k][i] - R->p[k][i] + R->n[k][i];
+            if (fabs(hv) > cv) cv = fabs(hv);
+            lam1 += fabs(R->lam[k][i]);
+            UPD(RESTO_RHO + R->lam[k][i] - R->zn[k][i]);
+            UPD(RESTO_RHO - R->lam[k][i] - R->zp[k][i]);
+            CMP(R->n[k][i], R->zn[k][i]); CMP(R->p[k][i], R->zp[k][i]);
+        }
+    }
+    for (int k = 1; k <= N; k++) {
+        for (int i = 0; i < NX; i++) {
+            double v = eta * R->dRx[k][i] * R->dRx[k][i] * (s->x[k][i] - R->xR[k][i]) - R->lam[k - 1][i];
+            if (k < N)
+                for (int l = 0; l < NX; l++) v += s->st[k].A[l][i] * R->lam[k][l];
+            if (i >= 10) v += -s->zLw[k][i - 10] + s->zUw[k][i - 10];
+            UPD(v);
+        }
+        for (int j = 0; j < 3; j++) { CMP(s->x[k][10 + j] - s->wL, s->zLw[k][j]); CMP(s->wU - s->x[k][10 + j], s->zUw[k][j]); }
+    }
+#undef UPD
+#undef CMP
+    const int m = NX * N, nz = 2 * (NU * N + 3 * N) + 2 * NX * N;
+    double sd = fmax(100.0, (lam1 + z1) / (m + nz)) / 100.0;
+    double sc = fmax(100.0, z1 / nz) / 100.0;
+    return fmax(dinf / sd, fmax(cv, cmp / sc));
+}
+
+/* Returns 1 when a point acceptable to the original filter was found (s->x, s->u, bound multipliers and lam updated, *fcur_out set),
+ * 0 when the restoration phase itself fails (locally infeasible / its own line search fails / iteration limit). */
+static int restoration_phase(ipm_t *s, double mu_orig, double tau_orig, fentry *filt, int nfilt, double theta_max_orig, int *iter, int max_iter,
+                             int *nls, double *fcur_out)
+{
+    const int N = s->N;
+    const se3o_params *p = s->p;
+    resto_t *R = (resto_t *)calloc(1, sizeof(resto_t));
+    ipm_t *bk = (ipm_t *)malloc(sizeof(ipm_t));
+    memcpy(bk, s, sizeof(ipm_t));                                    /* the original iterate (multipliers are needed at the end) */
+    const double gamma_theta = 1e-5, gamma_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, eta_phi = 1e-8, kappa_soc = 0.99, kappa_resto = 0.9;
+    /* reference point, scaling D_R */
+    memcpy(R->xR, s->x, sizeof(R->xR)); memcpy(R->uR, s->u, sizeof(R->uR));
+    for (int k = 0; k <= N; k++)
+        for (int i = 0; i < NX; i++) R->dRx[k][i] = 1.0 / fmax(1.0, fabs(s->x[k][i]));
+    for (int k = 0; k < N; k++)
+        for (int j = 0; j < NU; j++) R->dRu[k][j] = 1.0 / fmax(1.0, fabs(s->u[k][j]));
+    const double theta_orig0 = theta_of(s, s->c);
+    const double f_orig0 = nlp_objective(s, s->x, s->u, NULL, NULL);
+    const double phi_orig0 = barrier_obj(s, s->x, s->u, mu_orig, f_orig0);
+    /* initial restoration iterate (IpRestoIterateInitializer) */
+    double cinf = 0;
+    for (int k = 0; k < N; k++)
+        for (int i = 0; i < NX; i++) cinf = fmax(cinf, fabs(s->c[k][i]));
+    double mu = fmax(mu_orig, cinf), tau = fmax(0.99, 1.0 - mu);
+    for (int k = 0; k < N; k++)
+        for (int i = 0; i < NX; i++) {
+            const double c = s->c[k][i], a = (mu - RESTO_RHO * c) / (2.0 * RESTO_RHO);
+            R->n[k][i] = a + sqrt(a * a + mu * c / (2.0 * RESTO_RHO));
+            R->p[k][i] = c + R->n[k][i];
+            R->zn[k][i] = mu / R->n[k][i]; R->zp[k][i] = mu / R->p[k][i];
+        }
+    for (int k = 0; k < N; k++)
+        for (int j = 0; j < NU; j++) { s->zLu[k][j] = fmin(RESTO_RHO, s->zLu[k][j]); s->zUu[k][j] = fmin(RESTO_RHO, s->zUu[k][j]); }
+    for (int k = 1; k <= N; k++)
+        for (int j = 0; j < 3; j++) { s->zLw[k][j] = fmin(RESTO_RHO, s->zLw[k][j]); s->zUw[k][j] = fmin(RESTO_RHO, s->zUw[k][j]); }
+    /* least-squares multipliers of the restoration problem (constr_mult_init_max = 1e3): H = I on (y, n, p) -> D = 2 */
+    {
+        for (int k = 0; k < N; k++)
+            for (int i = 0; i < NX; i++) {
+                R->D[k][i] = 2.0;
+                R->chat[k][i] = (RESTO_RHO - R->zn[k][i]) - (RESTO_RHO - R->zp[k][i]);     /* g_n - g_p (see the derivation above) */
+            }
+        for (int k = 0; k <= N; k++)
+            for (int i = 0; i < NX; i++) R->gx[k][i] = (k >= 1 && i >= 10) ? -s->zLw[k][i - 10] + s->zUw[k][i - 10] : 0.0;
+        for (int k = 0; k < N; k++)
+            for (int j = 0; j < NU; j++) R->gu[k][j] = -s->zLu[k][j] + s->zUu[k][j];
+        int ok = riccati_resto(s, R, 1, 1, 0.0, 0.0, s->dx, s->du, R->lamp);
+        double lmax = 0;
+        for (int k = 0; k < N; k++)
+            for (int i = 0; i < NX; i++) lmax = fmax(lmax, fabs(R->lamp[k][i]));
+        if (ok && isfinite(lmax) && lmax <= 1e3) memcpy(R->lam, R->lamp, sizeof(R->lam));
+    }
+    const double mu_min = p->tol / 11.0;
+    fentry rf[FILT_MAX];
+    int nrf = 0, success = 0, first = 1;
+    double theta_r0 = resto_theta(s, s->c, R->n, R->p);
+    const double rtheta_max = 1e4 * fmax(1.0, theta_r0), rtheta_min = 1e-4 * fmax(1.0, theta_r0);
+    double delta_last = 0.0;
+    double (*sdx)[NX] = (double (*)[NX])malloc(sizeof(double) * NX * (NMAX + 1));
+    double (*sdu)[NU] = (double (*)[NU])malloc(sizeof(double) * NU * NMAX);
+    double (*slam)[NX] = (double (*)[NX])malloc(sizeof(double) * NX * NMAX);
+
+    for (;; (*iter)++) {
+        double eta = sqrt(mu);
+        /* 1. progress for the ORIGINAL problem (IpRestoConvCheck): not in the first restoration iteration */
+        if (!first) {
+            const double th_o = theta_of(s, s->c);
+            const double f_o = nlp_objective(s, s->x, s->u, NULL, NULL);
+            const double ph_o = barrier_obj(s, s->x, s->u, mu_orig, f_o);
+            int ok = isfinite(th_o) && isfinite(ph_o) && th_o <= kappa_resto * theta_orig0 && th_o <= theta_max_orig;
+            for (int e = 0; ok && e < nfilt; e++)
+                if (!(compare_le(th_o, filt[e].theta, filt[e].theta) || compare_le(ph_o, filt[e].phi, filt[e].phi))) ok = 0;
+            if (ok && !(compare_le(th_o, (1 - gamma_theta) * theta_orig0, theta_orig0) ||
+                        compare_le(ph_o - phi_orig0, -gamma_phi * theta_orig0, phi_orig0))) ok = 0;
+            if (ok) { success = 1; *fcur_out = f_o; break; }
+        }
+        first = 0;
+        if (*iter >= max_iter) break;
+        /* 2. restoration problem solved to tolerance without becoming acceptable: local infeasibility */
+        double E0 = resto_kkt_error(s, R, 0.0, eta);
+        if (!isfinite(E0) || E0 <= p->tol) break;
+        if (getenv("SE3O_VERBOSE"))
+            fprintf(stderr, "it %3dr fR=%.6e E0=%.3e mu=%.2e th_orig=%.3e th_R=%.3e\n", *iter, resto_objective(s, R, s->x, s->u, R->n, R->p, eta), E0, mu,
+                    theta_of(s, s->c), resto_theta(s, s->c, R->n, R->p));
+        /* 3. monotone barrier update */
+        for (;;) {
+            double Emu = resto_kkt_error(s, R, mu, sqrt(mu));
+            if (!(Emu <= 10.0 * mu) || mu <= mu_min) break;
+            double nm = fmax(mu_min, fmin(0.2 * mu, pow(mu, 1.5)));
+            if (nm == mu) break;
+            mu = nm; tau = fmax(0.99, 1.0 - mu); nrf = 0;
+        }
+        eta = sqrt(mu);
+        /* 4. Newton system */
+        for (int k = 0; k < N; k++)
+            for (int i = 0; i < NX; i++) {
+                const double sn = R->zn[k][i] / R->n[k][i], sp = R->zp[k][i] / R->p[k][i];
+                const double rn = RESTO_RHO + R->lam[k][i] - mu / R->n[k][i], rp = RESTO_RHO - R->lam[k][i] - mu / R->p[k][i];
+                R->D[k][i] = 1.0 / sn + 1.0 / sp;
+                R->h[k][i] = s->c[k][i] - R->p[k][i] + R->n[k][i];
+                R->chat[k][i] = R->h[k][i] - rn / sn + rp / sp + R->D[k][i] * R->lam[k][i];
+            }
+        for (int k = 0; k <= N; k++)
+            for (int i = 0; i < NX; i++) {
+                double g = (k >= 1) ? eta * R->dRx[k][i] * R->dRx[k][i] * (s->x[k][i] - R->xR[k][i]) : 0.0;
+                if (k >= 1 && i >= 10) { double sl = s->x[k][i] - s->wL, su = s->wU - s->x[k][i]; g += -mu / sl + mu / su; }
+                R->gx[k][i] = g;
+            }
+        for (int k = 0; k < N; k++)
+            for (int j = 0; j < NU; j++) {
+                double sl = s->u[k][j] - s->uL, su = s->uU - s->u[k][j];
+                R->gu[k][j] = eta * R->dRu[k][j] * R->dRu[k][j] * (s->u[k][j] - R->uR[k][j]) - mu / sl + mu / su;
+            }
+        double delta = 0.0;
+        int ok = 0;
+        for (;;) {
+            ok = riccati_resto(s, R, 0, 1, delta, eta, s->dx, s->du, R->lamp);
+            if (ok && !all_finite(&s->dx[0][0], NX * (N + 1))) ok = 0;
+            if (ok) break;
+            if (delta == 0.0) delta = (delta_last == 0.0) ? 1e-4 : fmax(1e-20, delta_last / 3.0);
+            else delta = (delta_last == 0.0 || 1e5 * delta_last < delta) ? 100.0 * delta : 8.0 * delta;
+            if (delta > 1e20) break;
+        }
+        if (!ok) break;
+        if (delta > 0) delta_last = delta;
+        /* slack and multiplier steps */
+#define SLACK_STEPS(LAMP) do {                                                                                             \
+        for (int k = 0; k < N; k++)                                                                                        \
+            for (int i = 0; i < NX; i++) {                                                                                 \
+                const double sn = R->zn[k][i] / R->n[k][i], sp = R->zp[k][i] / R->p[k][i];                                 \
+                const double rn = RESTO_RHO + R->lam[k][i] - mu / R->n[k][i], rp = RESTO_RHO - R->lam[k][i] - mu / R->p[k][i]; \
+                const double dl = (LAMP)[k][i] - R->lam[k][i];                                                             \
+                R->dn[k][i] = -(rn + dl) / sn; R->dp[k][i] = -(rp - dl) / sp;                                              \
+                R->dzn[k][i] = mu / R->n[k][i] - R->zn[k][i] - sn * R->dn[k][i];                                           \
+                R->dzp[k][i] = mu / R->p[k][i] - R->zp[k][i] - sp * R->dp[k][i];                                           \
+            } } while (0)
+#define FTB_SLACK(a_, DN, DP) do {                                                                                         \
+        for (int k = 0; k < N; k++)                                                                                        \
+            for (int i = 0; i < NX; i++) {                                                                                 \
+                if ((DN)[k][i] < 0) { double v = -tau * R->n[k][i] / (DN)[k][i]; if (v < a_) a_ = v; }                     \
+                if ((DP)[k][i] < 0) { double v = -tau * R->p[k][i] / (DP)[k][i]; if (v < a_) a_ = v; }                     \
+            } } while (0)
+        SLACK_STEPS(R->lamp);
+        compute_dz(s, mu, s->dx, s->du);
+        double alpha_max = frac_to_bound_primal(s, s->dx, s->du, tau);
+        FTB_SLACK(alpha_max, R->dn, R->dp);
+        double alpha_z = frac_to_bound_dual(s, tau);
+        FTB_SLACK(alpha_z, R->dzn, R->dzp);          /* (same rule on z_n, z_p: step dz, value z) */
+        {   /* FTB_SLACK tested n/dn; redo for the multipliers proper */
+            alpha_z = frac_to_bound_dual(s, tau);
+            for (int k = 0; k < N; k++)
+                for (int i = 0; i < NX; i++) {
+                    if (R->dzn[k][i] < 0) { double v = -tau * R->zn[k][i] / R->dzn[k][i]; if (v < alpha_z) alpha_z = v; }
+                    if (R->dzp[k][i] < 0) { double v = -tau * R->zp[k][i] / R->dzp[k][i]; if (v < alpha_z) alpha_z = v; }
+                }
+        }
+        /* filter line search on the restoration problem */
+        const double theta_k = resto_theta(s, s->c, R->n, R->p);
+        const double f_k = resto_objective(s, R, s->x, s->u, R->n, R->p, eta);
+        const double phi_k = resto_barrier(s, s->x, s->u, R->n, R->p, mu, f_k);
+        double gphid = 0;
+        for (int k = 1; k <= N; k++)
+            for (int i = 0; i < NX; i++) gphid += R->gx[k][i] * s->dx[k][i];
+        for (int k = 0; k < N; k++) {
+            for (int j = 0; j < NU; j++) gphid += R->gu[k][j] * s->du[k][j];
+            for (int i = 0; i < NX; i++) gphid += (RESTO_RHO - mu / R->n[k][i]) * R->dn[k][i] + (RESTO_RHO - mu / R->p[k][i]) * R->dp[k][i];
+        }
+        double alpha_min;
+        {
+            double am = gamma_theta;
+            if (gphid < 0) {
+                am = fmin(am, gamma_phi * theta_k / (-gphid));
+                if (theta_k <= rtheta_min) am = fmin(am, pow(theta_k, s_theta) / pow(-gphid, s_phi));
+            }
+            alpha_min = 0.05 * am;
+        }
+        double alpha = alpha_max, alpha_test = alpha;
+        int accepted = 0, firsttrial = 1;
+        double (*ddx)[NX] = s->dx, (*ddu)[NU] = s->du, (*ddn)[NX] = R->dn, (*ddp)[NX] = R->dp;
+        double (*ct)[NX] = (double (*)[NX])malloc(sizeof(double) * NX * NMAX);
+#define RTRIAL(a_, DX, DU, DN, DP, theta_out, phi_out) do {                                                                \
+            for (int k = 0; k <= N; k++) for (int i = 0; i < NX; i++) s->xt[k][i] = s->x[k][i] + (a_) * (DX)[k][i];        \
+            for (int k = 0; k < N; k++) {                                                                                  \
+                for (int j = 0; j < NU; j++) s->ut[k][j] = s->u[k][j] + (a_) * (DU)[k][j];                                 \
+                for (int i = 0; i < NX; i++) { R->nt[k][i] = R->n[k][i] + (a_) * (DN)[k][i]; R->pt[k][i] = R->p[k][i] + (a_) * (DP)[k][i]; } \
+            }                                                                                                              \
+            nlp_constraints(s, s->xt, s->ut, ct);                                                                          \
+            theta_out = resto_theta(s, ct, R->nt, R->pt);                                                                  \
+            phi_out = resto_barrier(s, s->xt, s->ut, R->nt, R->pt, mu, resto_objective(s, R, s->xt, s->ut, R->nt, R->pt, eta)); \
+        } while (0)
+#define RACCEPT(theta_t_, phi_t_, ok_) do {                                                                                \
+            int a_ = 1;                                                                                                    \
+            if (!isfinite(theta_t_) || !isfinite(phi_t_)) a_ = 0;                                                          \
+            else if (theta_t_ > rtheta_max) a_ = 0;                                                                        \
+            else {                                                                                                         \
+                int ftype_ = (gphid < 0) && (alpha_test * pow(-gphid, s_phi) > pow(theta_k, s_theta));                     \
+                if (ftype_ && theta_k <= rtheta_min) a_ = compare_le(phi_t_ - phi_k, eta_phi * alpha_test * gphid, phi_k); \
+                else a_ = compare_le(theta_t_, (1 - gamma_theta) * theta_k, theta_k) || compare_le(phi_t_ - phi_k, -gamma_phi * theta_k, phi_k); \
+                for (int e_ = 0; a_ && e_ < nrf; e_++)                                                                     \
+                    if (!(compare_le(theta_t_, rf[e_].theta, rf[e_].theta) || compare_le(phi_t_, rf[e_].phi, rf[e_].phi))) a_ = 0; \
+            }                                                                                                              \
+            ok_ = a_;                                                                                                      \
+        } while (0)
+        double phi_acc = 0;
+        while (!accepted) {
+            (*nls)++;
+            double theta_t, phi_t;
+            RTRIAL(alpha, ddx, ddu, ddn, ddp, theta_t, phi_t);
+            alpha_test = alpha;
+            RACCEPT(theta_t, phi_t, accepted);
+            if (accepted) { phi_acc = phi_t; break; }
+            if (firsttrial && p->max_soc > 0 && theta_t >= theta_k) {
+                /* second-order correction: only the constraint residual of the reduced system changes, chat += (alpha h + h(trial)) - h */
+                double (*chat0)[NX] = (double (*)[NX])malloc(sizeof(R->chat));
+                double (*hs)[NX] = (double (*)[NX])malloc(sizeof(R->h));
+                memcpy(chat0, R->chat, sizeof(R->chat));
+                for (int k = 0; k < N; k++)
+                    for (int i = 0; i < NX; i++) hs[k][i] = alpha * R->h[k][i] + (ct[k][i] - R->pt[k][i] + R->nt[k][i]);
+                double theta_soc_old = theta_k, theta_tr = theta_t;
+                for (int it = 0; it < p->max_soc && !accepted; it++) {
+                    if (it > 0 && !(theta_tr <= kappa_soc * theta_soc_old)) break;
+                    theta_soc_old = theta_tr;
+                    for (int k = 0; k < N; k++)
+                        for (int i = 0; i < NX; i++) R->chat[k][i] = chat0[k][i] + hs[k][i] - R->h[k][i];
+                    riccati_resto(s, R, 0, 0, delta, eta, sdx, sdu, slam);
+                    /* slack steps of the corrected system: r_c is h_soc */
+                    double (*sdn)[NX] = (double (*)[NX])malloc(sizeof(R->dn)), (*sdp)[NX] = (double (*)[NX])malloc(sizeof(R->dp));
+                    for (int k = 0; k < N; k++)
+                        for (int i = 0; i < NX; i++) {
+                            const double sn = R->zn[k][i] / R->n[k][i], sp = R->zp[k][i] / R->p[k][i];
+                            const double rn = RESTO_RHO + R->lam[k][i] - mu / R->n[k][i], rp = RESTO_RHO - R->lam[k][i] - mu / R->p[k][i];
+                            const double dl = slam[k][i] - R->lam[k][i];
+                            sdn[k][i] = -(rn + dl) / sn; sdp[k][i] = -(rp - dl) / sp;
+                        }
+                    double a_soc = frac_to_bound_primal(s, sdx, sdu, tau);
+                    FTB_SLACK(a_soc, sdn, sdp);
+                    double phi2;
+                    RTRIAL(a_soc, sdx, sdu, sdn, sdp, theta_tr, phi2);
+                    int okk;
+                    RACCEPT(theta_tr, phi2, okk);
+                    if (okk) {
+                        accepted = 1; phi_acc = phi2; alpha = a_soc;
+                        memcpy(s->dx, sdx, sizeof(double) * NX * (N + 1)); memcpy(s->du, sdu, sizeof(double) * NU * N);
+                        memcpy(R->lamp, slam, sizeof(R->lamp));
+                        SLACK_STEPS(R->lamp);
+                        compute_dz(s, mu, s->dx, s->du);
+                        alpha_z = frac_to_bound_dual(s, tau);
+                        for (int k = 0; k < N; k++)
+                            for (int i = 0; i < NX; i++) {
+                                if (R->dzn[k][i] < 0) { double v = -tau * R->zn[k][i] / R->dzn[k][i]; if (v < alpha_z) alpha_z = v; }
+                                if (R->dzp[k][i] < 0) { double v = -tau * R->zp[k][i] / R->dzp[k][i]; if (v < alpha_z) alpha_z = v; }
+                            }
+                    } else {
+                        for (int k = 0; k < N; k++)
+                            for (int i = 0; i < NX; i++) hs[k][i] = a_soc * hs[k][i] + (ct[k][i] - R->pt[k][i] + R->nt[k][i]);
+                    }
+                    free(sdn); free(sdp);
+                }
+                memcpy(R->chat, chat0, sizeof(R->chat));
+                free(chat0); free(hs);
+                if (accepted) break;
+            }
+            firsttrial = 0;
+            alpha *= 0.5;
+            if (alpha < alpha_min) break;
+        }
+        free(ct);
+        if (!accepted) break;                 /* the restoration phase cannot restore itself: failure */
+        {   /* filter augmentation */
+            int ftype = (gphid < 0) && (alpha_test * pow(-gphid, s_phi) > pow(theta_k, s_theta));
+            int armijo = compare_le(phi_acc - phi_k, eta_phi * alpha_test * gphid, phi_k);
+            if (!ftype || !armijo) {
+                fentry e = {(1 - gamma_theta) * theta_k, phi_k - gamma_phi * theta_k};
+                int w_ = 0;
+                for (int i = 0; i < nrf; i++)
+                    if (!(rf[i].theta >= e.theta && rf[i].phi >= e.phi)) rf[w_++] = rf[i];
+                nrf = w_;
+                if (nrf < FILT_MAX) rf[nrf++] = e;
+            }
+        }
+        /* accept the step */
+        memcpy(s->x, s->xt, sizeof(double) * NX * (N + 1));
+        memcpy(s->u, s->ut, sizeof(double) * NU * N);
+        const double ks = 1e10;
+#define ZUPD(z, dz, slack) do { double zn_ = (z) + alpha_z * (dz); double sl_ = (slack);                      \
+            zn_ = fmax(fmin(zn_, ks * mu / sl_), mu / (ks * sl_)); (z) = zn_; } while (0)
+        for (int k = 0; k < N; k++) {
+            for (int i = 0; i < NX; i++) {
+                R->n[k][i] = R->nt[k][i]; R->p[k][i] = R->pt[k][i];
+                R->lam[k][i] += alpha * (R->lamp[k][i] - R->lam[k][i]);
+                ZUPD(R->zn[k][i], R->dzn[k][i], R->n[k][i]); ZUPD(R->zp[k][i], R->dzp[k][i], R->p[k][i]);
+            }
+            for (int j = 0; j < NU; j++) {
+                ZUPD(s->zLu[k][j], s->dzLu[k][j], s->u[k][j] - s->uL);
+                ZUPD(s->zUu[k][j], s->dzUu[k][j], s->uU - s->u[k][j]);
+            }
+        }
+        for (int k = 1; k <= N; k++)
+            for (int j = 0; j < 3; j++) {
+                ZUPD(s->zLw[k][j], s->dzLw[k][j], s->x[k][10 + j] - s->wL);
+                ZUPD(s->zUw[k][j], s->dzUw[k][j], s->wU - s->x[k][10 + j]);
+            }
+#undef ZUPD
+        eval_point(s);
+    }
+    free(sdx); free(sdu); free(slam);
+    if (success) {
+        /* back to the regular algorithm (MinC_1NrmRestorationPhase::PerformRestoration): equality multipliers are reset to zero
+         * (constr_mult_reset_threshold = 0); bound multipliers take the primal-dual step that belongs to the primal move,
+         * dz = (mu - z (s_new - s_old)) / s_old - z, with the fraction-to-the-boundary rule, and are all reset to 1 when any of
+         * them exceeds bound_mult_reset_threshold = 1000 */
+        memset(s->lam, 0, sizeof(s->lam));
+        double amax = 1.0, zmax = 0.0;
+#define DZ(zold, sold, snew) ((mu_orig - (zold) * ((snew) - (sold))) / (sold) - (zold))
+#define FT(zold, dz) do { if ((dz) < 0) { double v = -tau_orig * (zold) / (dz); if (v < amax) amax = v; } } while (0)
+        for (int pass = 0; pass < 2; pass++) {
+            for (int k = 0; k < N; k++)
+                for (int j = 0; j < NU; j++) {
+                    const double zl = bk->zLu[k][j], zu = bk->zUu[k][j];
+                    const double dl = DZ(zl, bk->u[k][j] - s->uL, s->u[k][j] - s->uL), dq = DZ(zu, s->uU - bk->u[k][j], s->uU - s->u[k][j]);
+                    if (pass == 0) { FT(zl, dl); FT(zu, dq); }
+                    else { s->zLu[k][j] = zl + amax * dl; s->zUu[k][j] = zu + amax * dq; zmax = fmax(zmax, fmax(s->zLu[k][j], s->zUu[k][j])); }
+                }
+            for (int k = 1; k <= N; k++)
+                for (int j = 0; j < 3; j++) {
+                    const double zl = bk->zLw[k][j], zu = bk->zUw[k][j];
+                    const double dl = DZ(zl, bk->x[k][10 + j] - s->wL, s->x[k][10 + j] - s->wL), dq = DZ(zu, s->wU - bk->x[k][10 + j], s->wU - s->x[k][10 + j]);
+                    if (pass == 0) { FT(zl, dl); FT(zu, dq); }
+                    else { s->zLw[k][j] = zl + amax * dl; s->zUw[k][j] = zu + amax * dq; zmax = fmax(zmax, fmax(s->zLw[k][j], s->zUw[k][j])); }
+                }
+        }
+#undef DZ
+#undef FT
+        if (zmax > 1e3) {
+            for (int k = 0; k < N; k++)
+                for (int j = 0; j < NU; j++) { s->zLu[k][j] = 1.0; s->zUu[k][j] = 1.0; }
+            for (int k = 1; k <= N; k++)
+                for (int j = 0; j < 3; j++) { s->zLw[k][j] = 1.0; s->zUw[k][j] = 1.0; }
+        }
+        eval_point(s);
+    } else {
+        const int nf = s->nfact;
+        memcpy(s, bk, sizeof(ipm_t));            /* failure: leave the iterate where the regular algorithm stopped */
+        s->nfact = nf;
+    }
+    free(bk); free(R);
+    return success;
+}
+
 int se3o_solve(const se3o_params *p, const se3o_problem *pb, se3o_solution *sol)
 {
     return se3o_solve_from(p, pb, NULL, NULL, sol);
@@ -950,7 +1556,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
     int acc_count = 0, status = 2, iter = 0;
     int nls = 0, nsoc = 0;
     int in_soft_resto = 0, soft_resto_counter = 0, nsoft = 0;
-    int consec_short = 0, max_consec_short = 0;       /* IPOPT's soft restoration phase (IpBacktrackingLineSearch.cpp) */
+    int consec_short = 0, max_consec_short = 0, nresto = 0;       /* IPOPT's soft restoration phase (IpBacktrackingLineSearch.cpp) */
     double fcur = nlp_objective(s, s->x, s->u, NULL, NULL);
 
     for (iter = 0;; iter++) {
@@ -1165,7 +1771,28 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
                 free(bk);
             }
         }
-        if (!accepted) { status = 3; break; }          /* IPOPT would now enter the feasibility restoration phase (not implemented) */
+        if (!accepted && (p->flags & SE3O_FLAG_RESTO)) {
+            /* feasibility restoration phase; the current point is added to the original filter first (IpFilterLSAcceptor::PrepareRestoPhaseStart) */
+            {
+                fentry e = {(1 - gamma_theta) * theta_k, phi_k - gamma_phi * theta_k};
+                int w_ = 0;
+                for (int i = 0; i < nfilt; i++)
+                    if (!(filt[i].theta >= e.theta && filt[i].phi >= e.phi)) filt[w_++] = filt[i];
+                nfilt = w_;
+                if (nfilt < FILT_MAX) filt[nfilt++] = e;
+            }
+            in_soft_resto = 0; soft_resto_counter = 0;
+            double f_new = fcur;
+            iter++;
+            if (restoration_phase(s, mu, tau, filt, nfilt, theta_max, &iter, p->max_iter, &nls, &f_new)) {
+                fcur = f_new;
+                nresto++;
+                iter--;                                  /* (the for-loop increments) */
+                continue;
+            }
+            iter--;
+        }
+        if (!accepted) { status = 3; break; }          /* restoration failed (or is switched off) */
         if (getenv("SE3O_VERBOSE3"))
             fprintf(stderr, "   ls: alpha_max=%.3e alpha=%.3e alpha_z=%.3e ntrial_total=%d gphid=%.3e theta_k=%.3e theta_t? nfilt=%d\n", alpha_max, alpha, alpha_z, nls, gphid, theta_k, nfilt);
 
@@ -1225,7 +1852,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
         for (int j = 0; j < 3 && k >= 1; j++) { sol->ZL[k * 17 + 10 + j] = s->zLw[k][j]; sol->ZU[k * 17 + 10 + j] = s->zUw[k][j]; }
     for (int k = 0; k < N; k++)
         for (int j = 0; j < NU; j++) { sol->ZL[k * 17 + NX + j] = s->zLu[k][j]; sol->ZU[k * 17 + NX + j] = s->zUu[k][j]; }
-    sol->status = status; sol->iters = iter; sol->nfact = s->nfact; sol->nls = nls; sol->nsoc = nsoc; sol->nresto = getenv("SE3O_STAT") ? max_consec_short : nsoft;
+    sol->status = status; sol->iters = iter; sol->nfact = s->nfact; sol->nls = nls; sol->nsoc = nsoc; sol->nresto = getenv("SE3O_STAT") ? max_consec_short : nresto + nsoft;
     sol->mu = mu;
     free(s);
     return status;
