@@ -571,14 +571,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) se3mpc_kkt_step_kernel(
             if (t.f2[d] >= 0) sbase[t.f2[d]] = w2;
         }
         if (t.f3 >= 0) sbase[t.f3] = r3;
-        if (lane < 13) sm.Rb[lane * se3::SR + se3::EH] = se3::row(c, se3::R_C + lane)[a.dump_stage];
         __syncwarp();
         double *o = a.dump + (size_t)pb * (16 * se3::SR + 24 * se3::SQ);
-        for (int e = lane; e < 16 * se3::SR; e += 32) o[e] = sm.Rb[e];
-        for (int e = lane; e < 24 * se3::SQ; e += 32) {
-            const int i = e / se3::SQ, j = e % se3::SQ;
-            o[16 * se3::SR + e] = (i < 16 && j >= se3::FXO) ? 0.0 : sm.Qa[e];      // (the FX block is sweep state, not part of the stage Hessian)
+        for (int e = lane; e < 16 * se3::SR; e += 32) {           // dense [16][SR] image of the transposed shared-memory operand
+            const int i = e / se3::SR, j = e % se3::SR;
+            o[e] = (j < 24) ? sm.Rb[se3::rbi(i, j)] : 0.0;
         }
+        for (int e = lane; e < 24 * se3::SQ; e += 32) o[16 * se3::SR + e] = sm.Qa[e];
     }
 }
 

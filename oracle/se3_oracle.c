@@ -1542,6 +1542,14 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
     int nls = 0, nsoc = 0;
     int in_soft_resto = 0, soft_resto_counter = 0, nsoft = 0;
     int consec_short = 0, max_consec_short = 0, nresto = 0;       /* IPOPT's soft restoration phase (IpBacktrackingLineSearch.cpp) */
+    /* IPOPT's watchdog (IpBacktrackingLineSearch.cpp StartWatchDog / StopWatchDog; FilterLSAcceptor reference values): after
+     * watchdog_shortened_iter_trigger = 10 consecutive iterations whose accepted step needed backtracking, the full fraction-to-the-
+     * boundary step is taken WITHOUT an acceptance test for up to watchdog_trial_iter_max = 3 iterations; every trial point is
+     * tested against the point where the watchdog started (reference theta, phi, grad(phi)^T d).  If none is acceptable the
+     * iterate and the search direction of the starting point are restored and the backtracking resumes at alpha_max / 2. */
+    int in_watchdog = 0, wd_short = 0, wd_trial = 0, nwatch = 0;
+    double wd_theta = 0, wd_phi = 0, wd_gphid = 0, wd_fcur = 0, wd_delta = 0;
+    ipm_t *wd_save = NULL;
     double fcur = nlp_objective(s, s->x, s->u, NULL, NULL);
 
     for (iter = 0;; iter++) {
@@ -1566,6 +1574,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
             if (nm == mu) break;
             mu = nm; tau = fmax(0.99, 1.0 - mu);
             nfilt = 0;
+            in_watchdog = 0; wd_short = 0;                 /* BacktrackingLineSearch::Reset(): the watchdog is switched off, the iterate stays */
         }
 
         /* search direction with inertia correction */
@@ -1605,11 +1614,22 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
             }
             alpha_min = 0.05 * am;
         }
-        double alpha = alpha_max;
+        /* wake the watchdog up? */
+        if ((p->flags & SE3O_FLAG_WATCHDOG) && !in_watchdog && !in_soft_resto && wd_short >= 10) {
+            in_watchdog = 1; wd_trial = 0; nwatch++;
+            if (!wd_save) wd_save = (ipm_t *)malloc(sizeof(ipm_t));
+            memcpy(wd_save, s, sizeof(ipm_t));
+            wd_theta = theta_k; wd_phi = phi_k; wd_gphid = gphid; wd_fcur = fcur; wd_delta = delta;
+        }
+        int forced = 0, skip_first = 0, n_steps = 0;
+    line_search:
+        if (in_watchdog) { theta_k = wd_theta; phi_k = wd_phi; gphid = wd_gphid; }      /* InitThisLineSearch(in_watchdog): reference values */
+        double alpha = skip_first ? 0.5 * alpha_max : alpha_max;
         int accepted = 0, first = 1;
         double (*ddx)[NX] = s->dx, (*ddu)[NU] = s->du;
         double alpha_test = alpha;
         double ftrial = 0;
+        n_steps = 0;
         while (!accepted && !in_soft_resto) {
             nls++;
             for (int k = 0; k <= N; k++)
@@ -1644,8 +1664,9 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
                 fprintf(stderr, "      trial alpha=%.3e theta_t=%.6e (theta_k %.6e) phi_t=%.8e (phi_k %.8e) gphid=%.3e alpha_min=%.3e acc=%d\n", alpha, theta_t,
                         theta_k, phi_t, phi_k, gphid, alpha_min, accepted);
             if (accepted) break;
+            if (in_watchdog) break;                        /* only the full step is tried */
             /* second-order correction (first trial only, constraint violation not reduced) */
-            if (first && p->max_soc > 0 && theta_t >= theta_k) {
+            if (first && !skip_first && p->max_soc > 0 && theta_t >= theta_k) {
                 rhs_t *r2 = (rhs_t *)malloc(sizeof(rhs_t));
                 memcpy(r2, &s->rhs, sizeof(rhs_t));
                 double (*sdx)[NX] = (double (*)[NX])malloc(sizeof(double) * NX * (NMAX + 1));
@@ -1691,9 +1712,34 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
             }
             first = 0;
             alpha *= 0.5;
+            n_steps++;
             if (alpha < alpha_min) break;
         }
         (void)ddx; (void)ddu;
+        if (in_watchdog) {
+            if (accepted) in_watchdog = 0;                  /* "W": the watchdog procedure was successful */
+            else if (++wd_trial > 3) {
+                /* StopWatchDog: back to the stored iterate and direction, backtracking resumes below the full step */
+                const int nfact_keep = s->nfact;
+                memcpy(s, wd_save, sizeof(ipm_t));
+                s->nfact = nfact_keep;
+                in_watchdog = 0; wd_short = 0;
+                fcur = wd_fcur; delta = wd_delta;
+                theta_k = wd_theta; phi_k = wd_phi; gphid = wd_gphid;
+                alpha_max = frac_to_bound_primal(s, s->dx, s->du, tau);
+                alpha_z = frac_to_bound_dual(s, tau);
+                {
+                    double am = gamma_theta;
+                    if (gphid < 0) {
+                        am = fmin(am, gamma_phi * theta_k / (-gphid));
+                        if (theta_k <= theta_min) am = fmin(am, pow(theta_k, s_theta) / pow(-gphid, s_phi));
+                    }
+                    alpha_min = 0.05 * am;
+                }
+                skip_first = 1;
+                goto line_search;
+            } else { forced = 1; accepted = 1; }             /* "w": take the step anyway */
+        }
         if (!accepted && (p->flags & SE3O_FLAG_SOFT_RESTO)) {
             /* The backtracking line search ran below alpha_min (or the soft restoration phase is already active): IPOPT tries a
              * "soft restoration" step before it calls the restoration phase proper (TrySoftRestoStep): the ORIGINAL direction with
@@ -1782,8 +1828,9 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
             fprintf(stderr, "   ls: alpha_max=%.3e alpha=%.3e alpha_z=%.3e ntrial_total=%d gphid=%.3e theta_k=%.3e theta_t? nfilt=%d\n", alpha_max, alpha, alpha_z, nls, gphid, theta_k, nfilt);
 
         if (alpha < alpha_max) { consec_short++; if (consec_short > max_consec_short) max_consec_short = consec_short; } else consec_short = 0;
-        /* filter augmentation (uses the original alpha_test / direction) */
-        {
+        if (n_steps == 0) wd_short = 0; else wd_short++;         /* watchdog_shortened_iter_ (a step accepted at the first trial, SOC included, resets it) */
+        /* filter augmentation (uses the original alpha_test / direction); a forced watchdog step leaves the filter alone */
+        if (!forced) {
             int ftype = (gphid < 0) && (alpha_test * pow(-gphid, s_phi) > pow(theta_k, s_theta));
             double phi_new = barrier_obj(s, s->xt, s->ut, mu, ftrial);
             int armijo = compare_le(phi_new - phi_k, eta_phi * alpha_test * gphid, phi_k);
@@ -1839,6 +1886,8 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
         for (int j = 0; j < NU; j++) { sol->ZL[k * 17 + NX + j] = s->zLu[k][j]; sol->ZU[k * 17 + NX + j] = s->zUu[k][j]; }
     sol->status = status; sol->iters = iter; sol->nfact = s->nfact; sol->nls = nls; sol->nsoc = nsoc; sol->nresto = getenv("SE3O_STAT") ? max_consec_short : nresto + nsoft;
     sol->mu = mu;
+    if (getenv("SE3O_STAT_WD")) sol->nresto = nwatch;
+    free(wd_save);
     free(s);
     return status;
 }

@@ -19,3 +19,7 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 a.record(); r = se3.ops.objective(*args); b.record(); torch.cuda.synchronize()
 print("B", B, "ms", a.elapsed_time(b), "converged", int((r["status"] <= 1).sum()), "iters mean", float(r["iters"].double().mean()),
       "nfact mean", float(r["nfact"].double().mean()))
+it = r["iters"].cpu().numpy(); nf = r["nfact"].cpu().numpy()
+import numpy as np
+top = np.argsort(-nf)[:5]
+print("top nfact problems", top.tolist(), "nfact", nf[top].tolist(), "iters", it[top].tolist())

@@ -10,7 +10,8 @@ counts differ by one).  The north_star tolerance for trajectories (1e-5) sits ex
   * identical status vectors; solves that end in a different stationary point (cost differs by more than 1e-6 relative, or the
     trajectories by more than the tolerance ball 5e-5) are COUNTED and bounded: <= 0.1%, none with a cost difference above 1e-4;
   * >= 99.7% of all problems within every north_star tolerance (cost 1e-6, X/U 1e-5, reward 1e-6);
-  * every other problem within 5e-5 (the tolerance ball of tol = 1e-8), each with a different iteration count on the two sides;
+  * every other problem within 5e-5 (the tolerance ball of tol = 1e-8), each with a different iteration count on the two sides (or,
+    at identical counts, missing only the reward tolerance by the reward's 400-per-metre sensitivity to the trajectory);
   * re-solved at tol = 1e-10 on both sides, the misses -- and a 1024-problem batch -- agree to 1e-6 (typically 1e-9): the two
     implementations converge to the same point; the residual difference at the reference tolerance is the stopping rule's."""
 import numpy as np
@@ -71,7 +72,12 @@ def test_census_4096_at_the_reference_tolerance(oracle, se3):
     assert len(oth) <= 4                                            # <= 0.1% end in a different (nearby) stationary point
     assert len(miss) <= 12 and within.sum() >= 0.997 * conv.sum()
     assert dR[same].max() <= 2e-5
-    assert np.all(g["iters"][miss] != so["iters"][miss]), "a miss with identical iteration counts is not the stopping rule"
+    # a miss is the stopping rule's (different iteration counts) -- or, at identical iteration counts, a reward-only miss: the reward
+    # weighs the gate margin with 1000 * 2 * d_min = 400 per metre of rotor-tip displacement (quad_policy.py:90, solid_geometry.py:160),
+    # so trajectories that agree to 2e-6 can differ by 1e-6 (relative) in the reward of a colliding fly-through
+    same_cnt = miss[g["iters"][miss] == so["iters"][miss]]
+    assert np.all(dX[same_cnt] <= 1e-5) and np.all(dU[same_cnt] <= 1e-5), "a trajectory miss with identical iteration counts is not the stopping rule"
+    assert np.all(dR[same_cnt] <= 1e3 * dX[same_cnt])
     same_it = same & (g["iters"] == so["iters"])
     assert dX[same_it].max() <= 1e-5 and dU[same_it].max() <= 1e-5
     assert (np.abs(g["iters"] - so["iters"]) <= 2).mean() >= 0.99
