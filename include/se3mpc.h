@@ -74,6 +74,7 @@ typedef struct {
 
 #define SE3MPC_FLAG_SCALING 1   /* gradient-based objective scaling (IPOPT nlp_scaling_method default) */
 #define SE3MPC_FLAG_LSINIT  2   /* least-squares initial equality multipliers */
+#define SE3MPC_FLAG_RESTO   8   /* IPOPT's feasibility restoration phase when the filter line search fails (on by default in IPOPT) */
 
 /* Optional per-problem solver statistics (device or host int32/double arrays; any may be NULL). */
 typedef struct {

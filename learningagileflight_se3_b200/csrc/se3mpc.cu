@@ -45,13 +45,16 @@ struct KArgs {
     int32_t *status, *iters, *nfact, *nls;
     double *kkt_error;
     double *slots;
-    unsigned int *ticket;
+    unsigned int *ticket;      // [0] ticket of the main pass, [1] number of problems queued for the restoration pass, [2] its ticket
     const int32_t *order;      // longest-predicted-first processing order (or nullptr)
+    int32_t *redo;             // problems whose line search failed in the main pass (the restoration pass re-solves them)
 };
 
 // Instantiated for 2 and for CTAS_PER_SM resident CTAs per SM: the launch bound sets the register budget (255 vs 168), and the
 // host picks the instance by batch size (ctas_per_sm_for).
-template <int CTAS>
+// RESTO = false: the throughput pass.  RESTO = true: the second pass over the problems the first one queued in a.redo -- the same
+// solve from the start (deterministic: it fails its line search at the same iterate) with IPOPT's restoration phase compiled in.
+template <int CTAS, bool RESTO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,12 +67,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(
     c.ws = a.slots + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * se3::SLOT_DOUBLES;
     const int N = a.par.N;
 
+    const unsigned nwork = RESTO ? (unsigned)se3::uni((int)a.ticket[1]) : (unsigned)a.nprob;
     for (;;) {
         unsigned int pb = 0;
-        if (lane == 0) pb = atomicAdd(a.ticket, 1u);
+        if (lane == 0) pb = atomicAdd(a.ticket + (RESTO ? 2 : 0), 1u);
         pb = __shfl_sync(0xffffffffu, pb, 0);
-        if (pb >= (unsigned)a.nprob) break;
-        if (a.order) pb = (unsigned)se3::uni((int)a.order[pb]);      // (a loaded value is not provably warp-uniform: se3mpc_core.cuh, uni())
+        if (pb >= nwork) break;
+        if (RESTO) pb = (unsigned)se3::uni((int)a.redo[pb]);
+        else if (a.order) pb = (unsigned)se3::uni((int)a.order[pb]);      // (a loaded value is not provably warp-uniform: se3mpc_core.cuh, uni())
 
         // ---- instance (uniform registers) ----
         int src = (int)pb, variant = 0;
@@ -104,7 +109,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(
         in.xinit = a.Xinit ? a.Xinit + (size_t)pb * (N + 1) * 13 : nullptr;
         in.uinit = a.Uinit ? a.Uinit + (size_t)pb * N * 4 : nullptr;
 
-        const se3::SolveStats st = se3::ipm_solve(c, a.par, in);
+        const se3::SolveStats st = se3::ipm_solve<RESTO>(c, a.par, in);
+        if (!RESTO && st.want_resto && lane == 0) a.redo[atomicAdd(a.ticket + 1, 1u)] = (int32_t)pb;
 
         se3::write_outputs(c, a.X ? a.X + (size_t)pb * (N + 1) * 13 : nullptr, a.U ? a.U + (size_t)pb * N * 4 : nullptr,
                            a.LAM ? a.LAM + (size_t)pb * N * 13 : nullptr);
@@ -643,10 +649,12 @@ int device_setup()
     if (dev < 0 || dev >= MAX_DEVICES) return fail(SE3MPC_ERR_INVALID, "device index out of range");
     std::lock_guard<std::mutex> lk(mu);
     if (done[dev]) return SE3MPC_OK;
-    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
         return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<2>)", e);
-    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
         return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS>)", e);
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<2, resto>)", e);
     if ((e = cudaFuncSetAttribute(se3mpc_kkt_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
         return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_kkt_step_kernel)", e);
     if ((e = cudaFuncSetAttribute(se3mpc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM)) != cudaSuccess)
@@ -683,7 +691,7 @@ bool params_ok(const se3mpc_params *p)
 }
 
 // workspace: [ticket | pad to 256 B][aux doubles: nprob][aux int32: nprob][slots]
-struct WsLayout { unsigned int *ticket; double *aux_d; int32_t *aux_i, *lpt_hist, *lpt_key, *lpt_order; double *slots; int nslots; size_t bytes; };
+struct WsLayout { unsigned int *ticket; double *aux_d; int32_t *aux_i, *lpt_hist, *lpt_key, *lpt_order, *redo; double *slots; int nslots; size_t bytes; };
 
 WsLayout layout(void *ws, int nproblems)
 {
@@ -700,6 +708,8 @@ WsLayout layout(void *ws, int nproblems)
     L.lpt_key = reinterpret_cast<int32_t *>(b + off);
     off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
     L.lpt_order = reinterpret_cast<int32_t *>(b + off);
+    off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
+    L.redo = reinterpret_cast<int32_t *>(b + off);
     off += ((size_t)nproblems * sizeof(int32_t) + 255) / 256 * 256;
     L.slots = reinterpret_cast<double *>(b + off);
     L.nslots = slots_for(nproblems);
@@ -725,8 +735,8 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     a.Xinit = Xinit; a.Uinit = Uinit;
     if (stats) { a.status = stats->status; a.iters = stats->iters; a.nfact = stats->nfact; a.nls = stats->nls; a.kkt_error = stats->kkt_error; }
     if (status_override) a.status = status_override;
-    a.slots = L.slots; a.ticket = L.ticket;
-    CK(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), stream));
+    a.slots = L.slots; a.ticket = L.ticket; a.redo = L.redo;
+    CK(cudaMemsetAsync(L.ticket, 0, 4 * sizeof(unsigned int), stream));
     static const bool lpt_off = (getenv("SE3MPC_NO_LPT") != nullptr);      // A/B switch for profiling
     if (nprob > L.nslots && !lpt_off) {     // more problems than resident warps: longest-predicted-first order
         CK(cudaMemsetAsync(L.lpt_hist, 0, LPT_BUCKETS * sizeof(int32_t), stream));
@@ -741,10 +751,18 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     const size_t smem = SOLVER_SMEM;
     { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) return rc_attr; }
     const int grid = L.nslots / WARPS_PER_CTA;
-    if (ctas_per_sm_for(nprob) <= 2) se3mpc_solve_kernel<2><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
-    else se3mpc_solve_kernel<CTAS_PER_SM><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    if (ctas_per_sm_for(nprob) <= 2) se3mpc_solve_kernel<2, false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    else se3mpc_solve_kernel<CTAS_PER_SM, false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
     g_launches++;
     CK(cudaGetLastError());
+    if (p->flags & SE3MPC_FLAG_RESTO) {
+        // restoration pass over the problems whose line search failed (usually none: every warp reads the count and leaves).  The
+        // grid is at most two CTAs per SM; the slots of the main pass are reused.
+        const int cap2 = num_sms() * 2;
+        se3mpc_solve_kernel<2, true><<<grid < cap2 ? grid : cap2, WARPS_PER_CTA * 32, smem, stream>>>(a);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
     return SE3MPC_OK;
 }
 
@@ -768,7 +786,7 @@ void se3mpc_default_params(se3mpc_params *p)
     p->att_power = 2;                                                                                 // quad_model.py:210
     p->tol = 1e-8; p->acceptable_tol = 1e-6; p->mu_init = 0.1;                                        // IPOPT defaults
     p->max_iter = 3000; p->acceptable_iter = 15; p->max_soc = 4;
-    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT;
+    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT | SE3MPC_FLAG_RESTO;
 }
 
 const char *se3mpc_last_error(void) { return g_err; }

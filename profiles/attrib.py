@@ -12,8 +12,8 @@ elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True)
 funcs = [(0, "solve_kernel body (ipm loop, reward, init)")]
 # the solver kernel is instantiated twice (se3mpc_solve_kernel<2>, <3>): pick the instance the capture is of
 first = open(src_csv).readline()
-inst = re.search(r"solve_kernel<(?:\(int\))?(\d)>", first)
-tag = f"solve_kernelILi{inst.group(1)}E" if inst else "solve_kernel"
+inst = re.search(r"solve_kernel<(?:\(int\))?(\d)(?:, (?:\(bool\))?(\d))?>", first)
+tag = f"solve_kernelILi{inst.group(1)}ELb{inst.group(2) or 0}E" if inst else "solve_kernel"      # <CTAS, RESTO>
 for line in elf.split("\n"):
     if tag not in line:
         continue

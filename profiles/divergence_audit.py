@@ -11,7 +11,7 @@ KEYS = ("total", "R2UR", "BRA.DIV", "WARPSYNC", "LDCU", "BSSY", "UMOV", "NOP")
 
 def audit(lib="learningagileflight_se3_b200/csrc/libse3mpc.so", inst="2"):
     """{function name: Counter of KEYS} for se3mpc_solve_kernel<inst> (the kernel body is 'kernel body')."""
-    tag = f"solve_kernelILi{inst}E"
+    tag = f"solve_kernelILi{inst}ELb0E" if not str(inst).endswith("r") else f"solve_kernelILi{str(inst)[:-1]}ELb1E"      # "2r": the restoration-pass instance
     elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True, check=True).stdout
     funcs = [(0, "kernel body")]
     for line in elf.split("\n"):

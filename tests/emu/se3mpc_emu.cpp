@@ -39,7 +39,7 @@ extern "C" int se3emu_solve(const se3mpc_params *p, const double *x0, const doub
     make_ctx(c, p);
     Instance in;
     make_instance(x0, goal, tra_pos, tra_ang, t, ulast, round_t, in);
-    SolveStats st = ipm_solve(c, *p, in);
+    SolveStats st = ipm_solve<true>(c, *p, in);
     write_outputs(c, X, U, LAM);
     if (cost) *cost = st.cost;
     if (stats4) { stats4[0] = st.status; stats4[1] = st.iters; stats4[2] = st.nfact; stats4[3] = st.nls; }
