@@ -52,11 +52,18 @@ struct KArgs {
 
 // Instantiated for 2 and for CTAS_PER_SM resident CTAs per SM: the launch bound sets the register budget (255 vs 168), and the
 // host picks the instance by batch size (ctas_per_sm_for).
-// RESTO = false: the throughput pass.  RESTO = true: the second pass over the problems the first one queued in a.redo -- the same
-// solve from the start (deterministic: it fails its line search at the same iterate) with IPOPT's restoration phase compiled in.
-template <int CTAS, bool RESTO>
+// FULL: IPOPT's restoration phase and watchdog are compiled in (se3mpc_resto.cuh).  The default build is single-pass: the throughput
+// kernels are FULL.  -DSE3_TWO_PASS=1 builds them without (FULL = false) and adds a second-pass instance (REDO = true) that re-solves,
+// from the start, the problems the first pass queued in a.redo (failed line search / watchdog wake-up); kept for A/B measurements
+// of what the extra code costs the throughput path (profiles/README.md).
+#ifndef SE3_TWO_PASS
+#define SE3_TWO_PASS 0
+#endif
+constexpr bool TWO_PASS = SE3_TWO_PASS != 0;
+template <int CTAS, bool FULL, bool REDO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(const __grid_constant__ KArgs a)
 {
+    constexpr bool RESTO = REDO;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTA-shared per-lane work table (identical for every warp), then one WarpSmem per warp
     if (warp == 0) se3::make_lane_tab(lane, reinterpret_cast<se3::LaneTab *>(se3_smem_raw)[lane]);
@@ -109,8 +116,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(
         in.xinit = a.Xinit ? a.Xinit + (size_t)pb * (N + 1) * 13 : nullptr;
         in.uinit = a.Uinit ? a.Uinit + (size_t)pb * N * 4 : nullptr;
 
-        const se3::SolveStats st = se3::ipm_solve<RESTO>(c, a.par, in);
-        if (!RESTO && st.want_resto && lane == 0) a.redo[atomicAdd(a.ticket + 1, 1u)] = (int32_t)pb;
+#ifndef SE3_HOT_WATCHDOG
+#define SE3_HOT_WATCHDOG 1
+#endif
+        const se3::SolveStats st = se3::ipm_solve<FULL, FULL || (SE3_HOT_WATCHDOG != 0)>(c, a.par, in);
+        if (!FULL && st.want_resto && lane == 0) a.redo[atomicAdd(a.ticket + 1, 1u)] = (int32_t)pb;
 
         se3::write_outputs(c, a.X ? a.X + (size_t)pb * (N + 1) * 13 : nullptr, a.U ? a.U + (size_t)pb * N * 4 : nullptr,
                            a.LAM ? a.LAM + (size_t)pb * N * 13 : nullptr);
@@ -649,12 +659,12 @@ int device_setup()
     if (dev < 0 || dev >= MAX_DEVICES) return fail(SE3MPC_ERR_INVALID, "device index out of range");
     std::lock_guard<std::mutex> lk(mu);
     if (done[dev]) return SE3MPC_OK;
-    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2, !TWO_PASS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
         return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<2>)", e);
-    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS_PER_SM, !TWO_PASS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
         return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<CTAS>)", e);
-    if ((e = cudaFuncSetAttribute(se3mpc_solve_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
-        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<2, resto>)", e);
+    if (TWO_PASS && (e = cudaFuncSetAttribute(se3mpc_solve_kernel<2, true, TWO_PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
+        return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_solve_kernel<2, second pass>)", e);
     if ((e = cudaFuncSetAttribute(se3mpc_kkt_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVER_SMEM)) != cudaSuccess)
         return fail(SE3MPC_ERR_CUDA, "cudaFuncSetAttribute(se3mpc_kkt_step_kernel)", e);
     if ((e = cudaFuncSetAttribute(se3mpc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM)) != cudaSuccess)
@@ -751,15 +761,15 @@ int launch_solver(const se3mpc_params *p, int mode, int nprob, int round_t, cons
     const size_t smem = SOLVER_SMEM;
     { const int rc_attr = device_setup(); if (rc_attr != SE3MPC_OK) return rc_attr; }
     const int grid = L.nslots / WARPS_PER_CTA;
-    if (ctas_per_sm_for(nprob) <= 2) se3mpc_solve_kernel<2, false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
-    else se3mpc_solve_kernel<CTAS_PER_SM, false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    if (ctas_per_sm_for(nprob) <= 2) se3mpc_solve_kernel<2, !TWO_PASS, false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    else se3mpc_solve_kernel<CTAS_PER_SM, !TWO_PASS, false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
     g_launches++;
     CK(cudaGetLastError());
-    if (p->flags & SE3MPC_FLAG_RESTO) {
+    if (TWO_PASS && (p->flags & (SE3MPC_FLAG_RESTO | SE3MPC_FLAG_WATCHDOG))) {
         // restoration pass over the problems whose line search failed (usually none: every warp reads the count and leaves).  The
         // grid is at most two CTAs per SM; the slots of the main pass are reused.
         const int cap2 = num_sms() * 2;
-        se3mpc_solve_kernel<2, true><<<grid < cap2 ? grid : cap2, WARPS_PER_CTA * 32, smem, stream>>>(a);
+        se3mpc_solve_kernel<2, true, TWO_PASS><<<grid < cap2 ? grid : cap2, WARPS_PER_CTA * 32, smem, stream>>>(a);
         g_launches++;
         CK(cudaGetLastError());
     }
@@ -786,7 +796,7 @@ void se3mpc_default_params(se3mpc_params *p)
     p->att_power = 2;                                                                                 // quad_model.py:210
     p->tol = 1e-8; p->acceptable_tol = 1e-6; p->mu_init = 0.1;                                        // IPOPT defaults
     p->max_iter = 3000; p->acceptable_iter = 15; p->max_soc = 4;
-    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT | SE3MPC_FLAG_RESTO;
+    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT | SE3MPC_FLAG_RESTO | SE3MPC_FLAG_WATCHDOG;
 }
 
 const char *se3mpc_last_error(void) { return g_err; }

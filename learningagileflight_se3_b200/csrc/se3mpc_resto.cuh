@@ -438,6 +438,25 @@ SE3_BIG void resto_finish(const Ctx c, int success_, double mu_orig, double tau_
     }
 }
 
+// Watchdog (ipm_solve): iterate (rows R_X .. R_ZU) and search direction (R_DX .. R_LAMP) of the point where the watchdog starts are kept
+// in the restoration rows -- the two procedures never hold state at the same time (the watchdog is stopped before the restoration
+// phase is entered).  restore = 0: save, 1: put back.
+constexpr int WD_ROWS = R_SDX;          // rows [0, R_SDX): x, u, lam, zL, zU, dx, du, lam+
+static_assert(R_ALL - R_RN >= WD_ROWS, "the watchdog copy lives in the restoration rows");
+SE3_BIG void watchdog_rows(const Ctx c, int restore_)
+{
+    const int restore = uni(restore_);
+    WARP_FOR(lane) {
+#pragma unroll 1
+        for (int r = 0; r < WD_ROWS; r++) {
+            double *a = row(c, r), *b = row(c, R_RN + r);
+            if (restore) { a[lane] = b[lane]; a[lane + 32] = b[lane + 32]; }
+            else { b[lane] = a[lane]; b[lane + 32] = a[lane + 32]; }
+        }
+    }
+    WARP_SYNC();
+}
+
 /*
  * The restoration phase.  The caller has added the current point to the original filter (IpFilterLSAcceptor::PrepareRestoPhaseStart).
  * ok = 1 when a point acceptable to the original filter was found (iterate and multipliers updated, rows R_C and theta, f, logsum of
@@ -447,9 +466,22 @@ SE3_BIG void resto_finish(const Ctx c, int success_, double mu_orig, double tau_
 struct RestoOut { int ok, iter, nls; double theta, f, logsum; };
 SE3_HD RestoOut uni(RestoOut r) { r.ok = uni(r.ok); r.iter = uni(r.iter); r.nls = uni(r.nls); r.theta = uni(r.theta); r.f = uni(r.f); r.logsum = uni(r.logsum); return r; }
 
-SE3_HD RestoOut restoration_phase(const Ctx c, const se3mpc_params &par, double mu_orig, double tau_orig, int nfilt, double theta_max_orig,
-                                   double theta_orig0, double phi_orig0, double cinf0, int iter_in, int nls_in)
+#ifndef SE3_RESTO_INLINE
+#define SE3_RESTO_INLINE 0
+#endif
+#if SE3_RESTO_INLINE
+SE3_HD
+#else
+SE3_BIG           // out of line: the interior-point loop of the kernel body stays compact (single-warp latency: profiles/README.md)
+#endif
+RestoOut restoration_phase(const Ctx c, double tol_, int max_iter_, int max_soc_, double mu_orig_, double tau_orig_, int nfilt_, double theta_max_orig_,
+                           double theta_orig0_, double phi_orig0_, double cinf0_, int iter_in_, int nls_in_)
 {
+    // (arguments of a non-inlined function are not provably warp-uniform for ptxas: see uni())
+    const double mu_orig = uni(mu_orig_), tau_orig = uni(tau_orig_), theta_max_orig = uni(theta_max_orig_), theta_orig0 = uni(theta_orig0_);
+    const double phi_orig0 = uni(phi_orig0_), cinf0 = uni(cinf0_);
+    const int nfilt = uni(nfilt_), iter_in = uni(iter_in_), nls_in = uni(nls_in_), max_iter = uni(max_iter_), max_soc = uni(max_soc_);
+    const double tol = uni(tol_);
     int iter_v = iter_in, nls_v = nls_in;
     int *iter = &iter_v, *nls = &nls_v;
     double theta_o = 0.0, f_o = 0.0, logsum_o = 0.0;
@@ -460,18 +492,23 @@ SE3_HD RestoOut restoration_phase(const Ctx c, const se3mpc_params &par, double 
     const double gamma_theta = 1e-5, gamma_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, eta_phi = 1e-8, kappa_soc = 0.99, kappa_resto = 0.9;
     double mu = fmax(mu_orig, cinf0), tau = fmax(0.99, 1.0 - mu);
     resto_begin(c, mu);
-    const double mu_min = par.tol / 11.0;
+    const double mu_min = tol / 11.0;
     int nrf = 0, success = 0, first = 1;
     double delta_last = 0.0;
     double rtheta_max = 0.0, rtheta_min = 0.0;
 
     for (;; (*iter)++) {
+        // Loop-carried scalars are warp-uniform by construction, but ptxas cannot prove it across the back edge of THIS loop; one
+        // possibly-divergent value here and every phase of the solver is compiled divergence-safe (se3mpc_core.cuh, uni()).  A dozen
+        // REDUX per restoration iteration keep the throughput path clean (tests/test_codegen.py).
+        mu = uni(mu); tau = uni(tau); delta_last = uni(delta_last); nrf = uni(nrf); rtheta_max = uni(rtheta_max); rtheta_min = uni(rtheta_min);
+        first = uni(first); iter_v = uni(iter_v); nls_v = uni(nls_v);
         double eta = dsqrt(mu);
         // 1. progress for the ORIGINAL problem (IpRestoConvCheck): not in the first restoration iteration
         double th_o, ci_o;
         eval_constraints(c, &th_o, &ci_o);
         th_o = uni(th_o);
-        if (!first) {
+        if (UNI(!first)) {          // (a loop-carried flag is not provably warp-uniform for ptxas: see uni())
             const TrialOut t0 = uni(eval_trial(c, 0.0, R_DX, R_DU, 0, 0.0));
             const double ph_o = sf * t0.f - mu_orig * t0.logsum;
             int ok = t0.feasible && (fabs(th_o) <= 1e300) && (fabs(ph_o) <= 1e300) && th_o <= kappa_resto * theta_orig0 && th_o <= theta_max_orig;
@@ -480,17 +517,17 @@ SE3_HD RestoOut restoration_phase(const Ctx c, const se3mpc_params &par, double 
             ok = ok && (compare_le(th_o, (1 - gamma_theta) * theta_orig0, theta_orig0) || compare_le(ph_o - phi_orig0, -gamma_phi * theta_orig0, phi_orig0));
             if (uni(ok)) { success = 1; *theta_out = th_o; *f_out = t0.f; *logsum_out = t0.logsum; break; }
         }
-        if (first) {
+        if (UNI(first)) {
             // theta of the restoration problem at its starting point (c - p + n = 0 by construction, up to rounding)
             const TrialOut tr0 = uni(resto_trial(c, 0.0, mu, eta, R_DX, R_DU, R_RLAM, 0, 0.0));
             rtheta_max = 1e4 * fmax(1.0, tr0.theta); rtheta_min = 1e-4 * fmax(1.0, tr0.theta);
         }
         first = 0;
-        if (*iter >= par.max_iter) break;
+        if (*iter >= max_iter) break;
         // 2. restoration problem solved to tolerance without becoming acceptable: local infeasibility
         RKktOut kk = uni(resto_kkt(c, mu, eta));
         const double E0 = resto_kkt_scaled(N, kk, kk.cmp0);
-        if (UNI(!(E0 <= 1e300) || E0 <= par.tol)) break;
+        if (UNI(!(E0 <= 1e300) || E0 <= tol)) break;
         // 3. monotone barrier update
         {
             double cmp = kk.cmpmu;
@@ -556,14 +593,14 @@ SE3_HD RestoOut restoration_phase(const Ctx c, const se3mpc_params &par, double 
         };
         while (!accepted) {
             (*nls)++;
-            const int want_soc = firsttrial && par.max_soc > 0;
+            const int want_soc = firsttrial && max_soc > 0;
             TrialOut tr = uni(resto_trial(c, alpha, mu, eta, R_DX, R_DU, R_LAMP, want_soc ? 1 : 0, alpha));
             alpha_test = alpha;
             accepted = acceptable(tr);
             if (accepted) { phi_acc = tr.f - mu * tr.logsum; break; }
             if (UNI(want_soc && tr.theta >= theta_k)) {
                 double theta_soc_old = theta_k, theta_tr = tr.theta;
-                for (int it = 0; it < par.max_soc && !accepted; it++) {
+                for (int it = 0; it < max_soc && !accepted; it++) {
                     if (UNI(it > 0 && !(theta_tr <= kappa_soc * theta_soc_old))) break;
                     theta_soc_old = theta_tr;
                     resto_soc_rows(c);

@@ -41,7 +41,7 @@ void se3o_default_params(se3o_params *p)
     p->att_power = 2;                                                                             /* quad_model.py:210 */
     p->tol = 1e-8; p->acceptable_tol = 1e-6; p->mu_init = 0.1;
     p->max_iter = 3000; p->acceptable_iter = 15; p->max_soc = 4;
-    p->flags = SE3O_FLAG_SCALING | SE3O_FLAG_LSINIT | SE3O_FLAG_RESTO;
+    p->flags = SE3O_FLAG_SCALING | SE3O_FLAG_LSINIT | SE3O_FLAG_RESTO | SE3O_FLAG_WATCHDOG;
 }
 
 /* quad_policy.py:10-13 Rd2Rp, quad_model.py:818-825 toQuaternion */

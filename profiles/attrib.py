@@ -12,8 +12,10 @@ elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True)
 funcs = [(0, "solve_kernel body (ipm loop, reward, init)")]
 # the solver kernel is instantiated twice (se3mpc_solve_kernel<2>, <3>): pick the instance the capture is of
 first = open(src_csv).readline()
-inst = re.search(r"solve_kernel<(?:\(int\))?(\d)(?:, (?:\(bool\))?(\d))?>", first)
-tag = f"solve_kernelILi{inst.group(1)}ELb{inst.group(2) or 0}E" if inst else "solve_kernel"      # <CTAS, RESTO>
+inst = re.search(r"solve_kernel<(?:\(int\))?(\d)", first)
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+from divergence_audit import kernel_tag  # noqa: E402
+tag = kernel_tag(elf, inst.group(1)) if inst else "solve_kernel"      # <CTAS, FULL, REDO = false>
 for line in elf.split("\n"):
     if tag not in line:
         continue

@@ -4,8 +4,10 @@ import collections, csv, re, subprocess, sys
 src_csv, lib = sys.argv[1], sys.argv[2]
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 first = open(src_csv).readline()
-inst = re.search(r"solve_kernel<(?:\(int\))?(\d)(?:, (?:\(bool\))?(\d))?>", first)
-tag = f"solve_kernelILi{inst.group(1)}ELb{inst.group(2) or 0}E"
+inst = re.search(r"solve_kernel<(?:\(int\))?(\d)", first)
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+from divergence_audit import kernel_tag  # noqa: E402
+tag = kernel_tag(elf, inst.group(1))
 funcs = [(0, "solve_kernel body")]
 for line in elf.split("\n"):
     if tag not in line: continue

@@ -5,7 +5,9 @@ args = sys.argv[1:]
 lib = next((a for a in args if a.endswith(".so")), "learningagileflight_se3_b200/csrc/libse3mpc.so")
 inst = next((a for a in args if a.isdigit()), "2")
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
-tag = f"solve_kernelILi{inst}ELb0E" if f"solve_kernelILi{inst}ELb0E" in elf else "solve_kernel"      # the throughput instance <CTAS, RESTO = false>
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+from divergence_audit import kernel_tag  # noqa: E402
+tag = kernel_tag(elf, inst)      # the throughput instance <CTAS, FULL, REDO = false>
 seen = {}
 for line in elf.split("\n"):
     m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+\S+\s+\S+\s+\S+\s+(\S*" + tag + r"\S*)", line)

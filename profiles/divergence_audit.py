@@ -9,10 +9,17 @@ import sys
 KEYS = ("total", "R2UR", "BRA.DIV", "WARPSYNC", "LDCU", "BSSY", "UMOV", "NOP")
 
 
+def kernel_tag(elf_text, inst, redo=0):
+    """mangled-name fragment of se3mpc_solve_kernel<inst, FULL, REDO = redo> as built (FULL depends on -DSE3_TWO_PASS)"""
+    import re as _re
+    names = sorted(set(_re.findall(r"solve_kernelILi%sELb[01]ELb%dE" % (inst, redo), elf_text)))
+    return names[0] if names else "solve_kernelILi%sE" % inst
+
+
 def audit(lib="learningagileflight_se3_b200/csrc/libse3mpc.so", inst="2"):
     """{function name: Counter of KEYS} for se3mpc_solve_kernel<inst> (the kernel body is 'kernel body')."""
-    tag = f"solve_kernelILi{inst}ELb0E" if not str(inst).endswith("r") else f"solve_kernelILi{str(inst)[:-1]}ELb1E"      # "2r": the restoration-pass instance
     elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True, check=True).stdout
+    tag = kernel_tag(elf, str(inst).rstrip("r"), 1 if str(inst).endswith("r") else 0)      # "2r": the second-pass instance of a -DSE3_TWO_PASS build
     funcs = [(0, "kernel body")]
     for line in elf.split("\n"):
         if tag not in line:

@@ -24,9 +24,11 @@ def test_solver_is_not_compiled_divergence_safe(instance):
     a = audit(LIB, instance)
     for f in UNIFORM_PHASES + STAGE_PARALLEL + ("kernel body",):
         assert f in a, (f, sorted(a))
+    for f in a:                                                     # every phase, the restoration phase's included (se3mpc_resto.cuh)
         assert a[f]["BRA.DIV"] == 0, (f, dict(a[f]))                # no divergence guards around shuffles
-        assert a[f]["WARPSYNC"] <= 2, (f, dict(a[f]))               # (WARPSYNC.ALL of __syncwarp is not emitted as such; COLLECTIVE wrappers are)
-    for f in UNIFORM_PHASES:
+        assert a[f]["WARPSYNC"] <= 4, (f, dict(a[f]))               # (WARPSYNC.ALL of __syncwarp is not emitted as such; COLLECTIVE wrappers are)
+    for f in UNIFORM_PHASES + tuple(f + "_soft" for f in UNIFORM_PHASES):
         assert a[f]["R2UR"] == 0 and a[f]["LDCU"] >= 1, (f, dict(a[f]))   # the memory descriptor comes from one LDCU per function
-    total = sum(c["total"] for c in a.values())
-    assert total < 15000, total                                     # 16.7 k instructions when everything was divergence-safe
+    hot = sum(a[f]["total"] for f in UNIFORM_PHASES + STAGE_PARALLEL)
+    assert hot < 8000, hot                                          # 16.7 k instructions (with the kernel body) when everything was divergence-safe
+    assert a["kernel body"]["total"] < 12000, a["kernel body"]["total"]   # interior-point loop + inlined restoration-phase control flow + reward
