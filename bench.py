@@ -158,6 +158,8 @@ def cpu_reference(batch, seed, nthreads=0):
     """The reference arm's engine: the CPU oracle (restated fp64 IPM + reward), one problem per host thread."""
     from oracle import oracle as O
     O.build()
+    global CPU_FLAGS
+    CPU_FLAGS = O.use_native()          # compiled for the host cores it is timed on (SURVEY.md 8(d))
     sc = sample_scenarios(batch, seed)
     p = O.default_params()
     t0 = time.perf_counter()
@@ -165,6 +167,9 @@ def cpu_reference(batch, seed, nthreads=0):
     dt = time.perf_counter() - t0
     conv = int(np.sum(r["status"] <= 1))
     return conv, dt, O.num_threads()
+
+
+CPU_FLAGS = ""
 
 
 def run_reference(args):
@@ -186,7 +191,7 @@ def run_reference(args):
                        "note": "CasADi/IPOPT (the reference's solver) is not installable offline; this arm times the repo's CPU restatement "
                                "of the same NLP + IPOPT-style interior point + reward on all host cores"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} problems of the configs[1] workload per step x {args.steps} steps"},
+                             "sample": f"{sample} problems of the configs[1] workload per step x {args.steps} steps", "build": "gcc " + CPU_FLAGS},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -462,7 +467,7 @@ def main():
             conv_c, dt_c, cores = cpu_reference(args.cpu_sample, 1)
             cpu_b = {"value": conv_c / dt_c, "unit": UNIT, "cores": cores, "kind": "port",
                      "sample": f"{args.cpu_sample} problems of the same workload (seed 1), {dt_c:.1f} s wall on {cores} threads; "
-                               "restated fp64 CPU IPM + reward (oracle/), not CasADi/IPOPT"}
+                               "restated fp64 CPU IPM + reward (oracle/), not CasADi/IPOPT", "build": "gcc " + CPU_FLAGS}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",

@@ -62,6 +62,44 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_native = None          # path of the -march=native build once use_native() switched to it
+
+
+def _cpu_tag() -> str:
+    """Short hash of this host's CPU model + ISA flags: a -march=native build is only valid on the CPU it was compiled on (the
+    repo snapshot, built .so files included, travels between the build container and the GPU box)."""
+    import hashlib
+    model, flags = "", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            if line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+            if model and flags:
+                break
+    except OSError:
+        pass
+    return hashlib.sha1((model + "|" + flags).encode()).hexdigest()[:10]
+
+
+def use_native() -> str:
+    """Switch to a build of the same source with `-O3 -march=native` for THIS host (the CPU baseline is compiled
+    for the cores it is timed on); compiled on first use, tagged with the CPU it belongs to.  Returns the compiler flags in use
+    (the portable x86-64-v3 build of the Makefile when the native build is not possible)."""
+    global _lib, _native, _LIB_PATH
+    if _native:
+        return "-O3 -march=native"
+    path = os.path.join(_HERE, f"libse3oracle_native_{_cpu_tag()}.so")
+    src = os.path.join(_HERE, "se3_oracle.c")
+    try:
+        if not os.path.exists(path) or os.path.getmtime(src) > os.path.getmtime(path):
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu11", "-shared", "-o", path, src, "-lm", "-lpthread"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        return "-O3 -march=x86-64-v3"
+    _LIB_PATH, _native, _lib = path, path, None
+    return "-O3 -march=native"
 
 
 def lib():
