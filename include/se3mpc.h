@@ -75,6 +75,7 @@ typedef struct {
 #define SE3MPC_FLAG_SCALING 1   /* gradient-based objective scaling (IPOPT nlp_scaling_method default) */
 #define SE3MPC_FLAG_LSINIT  2   /* least-squares initial equality multipliers */
 #define SE3MPC_FLAG_RESTO   8   /* IPOPT's feasibility restoration phase when the filter line search fails (on by default in IPOPT) */
+#define SE3MPC_FLAG_FILTER_RESET 32 /* IPOPT's filter reset heuristic (filter_reset_trigger = 5, max_filter_resets = 5; IPOPT default) */
 #define SE3MPC_FLAG_WATCHDOG 16 /* IPOPT's watchdog procedure (watchdog_shortened_iter_trigger = 10, watchdog_trial_iter_max = 3; IPOPT default) */
 
 /* Optional per-problem solver statistics (device or host int32/double arrays; any may be NULL). */

@@ -796,7 +796,7 @@ void se3mpc_default_params(se3mpc_params *p)
     p->att_power = 2;                                                                                 // quad_model.py:210
     p->tol = 1e-8; p->acceptable_tol = 1e-6; p->mu_init = 0.1;                                        // IPOPT defaults
     p->max_iter = 3000; p->acceptable_iter = 15; p->max_soc = 4;
-    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT | SE3MPC_FLAG_RESTO | SE3MPC_FLAG_WATCHDOG;
+    p->flags = SE3MPC_FLAG_SCALING | SE3MPC_FLAG_LSINIT | SE3MPC_FLAG_RESTO | SE3MPC_FLAG_WATCHDOG | SE3MPC_FLAG_FILTER_RESET;
 }
 
 const char *se3mpc_last_error(void) { return g_err; }

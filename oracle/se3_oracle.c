@@ -41,7 +41,7 @@ void se3o_default_params(se3o_params *p)
     p->att_power = 2;                                                                             /* quad_model.py:210 */
     p->tol = 1e-8; p->acceptable_tol = 1e-6; p->mu_init = 0.1;
     p->max_iter = 3000; p->acceptable_iter = 15; p->max_soc = 4;
-    p->flags = SE3O_FLAG_SCALING | SE3O_FLAG_LSINIT | SE3O_FLAG_RESTO | SE3O_FLAG_WATCHDOG;
+    p->flags = SE3O_FLAG_SCALING | SE3O_FLAG_LSINIT | SE3O_FLAG_RESTO | SE3O_FLAG_WATCHDOG | SE3O_FLAG_FILTER_RESET;
 }
 
 /* quad_policy.py:10-13 Rd2Rp, quad_model.py:818-825 toQuaternion */
@@ -1547,6 +1547,10 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
      * boundary step is taken WITHOUT an acceptance test for up to watchdog_trial_iter_max = 3 iterations; every trial point is
      * tested against the point where the watchdog started (reference theta, phi, grad(phi)^T d).  If none is acceptable the
      * iterate and the search direction of the starting point are restored and the backtracking resumes at alpha_max / 2. */
+    /* IPOPT's filter reset heuristic (filter_reset_trigger = 5, max_filter_resets = 5; IpFilterLSAcceptor.cpp): when in five
+     * successive iterations the last rejected trial step was rejected because of the filter, the filter is cleared (at most five
+     * times per solve).  Switch: SE3O_FLAG_FILTER_RESET. */
+    int rej_filter = 0, n_rej_filter = 0, n_filter_resets = 0;
     int in_watchdog = 0, wd_short = 0, wd_trial = 0, nwatch = 0;
     double wd_theta = 0, wd_phi = 0, wd_gphid = 0, wd_fcur = 0, wd_delta = 0;
     ipm_t *wd_save = NULL;
@@ -1575,6 +1579,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
             mu = nm; tau = fmax(0.99, 1.0 - mu);
             nfilt = 0;
             in_watchdog = 0; wd_short = 0;                 /* BacktrackingLineSearch::Reset(): the watchdog is switched off, the iterate stays */
+            rej_filter = 0; n_rej_filter = 0;               /* FilterLSAcceptor::Reset() */
         }
 
         /* search direction with inertia correction */
@@ -1653,9 +1658,10 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
                     else                                                                                     \
                         a_ = compare_le(theta_t_, (1 - gamma_theta) * theta_k, theta_k) ||                   \
                              compare_le(phi_t_ - phi_k, -gamma_phi * theta_k, phi_k);                        \
+                    if (!a_) rej_filter = 0;                   /* rejected by the test against the current iterate */    \
                     for (int e_ = 0; a_ && e_ < nfilt; e_++)                                                 \
                         if (!(compare_le(theta_t_, filt[e_].theta, filt[e_].theta) ||                        \
-                              compare_le(phi_t_, filt[e_].phi, filt[e_].phi))) a_ = 0;                       \
+                              compare_le(phi_t_, filt[e_].phi, filt[e_].phi))) { a_ = 0; rej_filter = 1; }   \
                 }                                                                                            \
                 ok_ = a_;                                                                                    \
             } while (0)
@@ -1829,6 +1835,13 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
 
         if (alpha < alpha_max) { consec_short++; if (consec_short > max_consec_short) max_consec_short = consec_short; } else consec_short = 0;
         if (n_steps == 0) wd_short = 0; else wd_short++;         /* watchdog_shortened_iter_ (a step accepted at the first trial, SOC included, resets it) */
+        if ((p->flags & SE3O_FLAG_FILTER_RESET) && !forced) {
+            if (rej_filter) {
+                n_rej_filter++;
+                if (n_filter_resets < 5 && n_rej_filter >= 5) { nfilt = 0; n_filter_resets++; n_rej_filter = 0; rej_filter = 0; }
+            } else
+                n_rej_filter = 0;
+        }
         /* filter augmentation (uses the original alpha_test / direction); a forced watchdog step leaves the filter alone */
         if (!forced) {
             int ftype = (gphid < 0) && (alpha_test * pow(-gphid, s_phi) > pow(theta_k, s_theta));
