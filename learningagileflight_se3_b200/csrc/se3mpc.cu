@@ -151,24 +151,41 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS) se3mpc_solve_kernel(
 
 // ---- longest-predicted-first ordering ------------------------------------------------------------------------------
 // The NLPs need 35..130 interior-point iterations; with more problems than resident warps the makespan is set by the
-// stragglers that start late.  A linear predictor of the factorisation count (fitted on 1500 synthetic scenarios,
-// correlation 0.69) buckets the problems; warps take tickets in descending-bucket order.  Results do not depend on the
+// stragglers that start late.  A predictor of the factorisation count (lpt_bucket) buckets the problems; warps take tickets in
+// descending-bucket order.  Results do not depend on the
 // order (every problem is solved by one warp with a fixed arithmetic order).
 constexpr int LPT_BUCKETS = 256;
 
+// Quadratic predictor of the factorisation count (profiles/lpt/fit_predictor.py: ridge regression on the 210 monomials of 19 standardised
+// instance features, 65 536 synthetic problems solved by the CPU oracle, held-out correlation 0.86; the linear four-feature predictor of
+// round 1 had 0.70).  Single precision: only the ORDER of the problems depends on it, never a result.
+#include "se3mpc_lpt_coef.h"
 __device__ __forceinline__ int lpt_bucket(const KArgs &a, int pb)
 {
     const int src = (a.mode == MODE_SOLGRAD) ? pb / 9 : pb;
     const double *x0 = a.x0 + (size_t)src * 13, *g = a.goal + (size_t)src * 3, *tp = a.tra_pos + (size_t)src * 3;
     const double *ta = a.tra_ang + (size_t)src * a.att_dim;
-    const double r0 = sqrt(x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2]);
-    const double dist = sqrt((x0[0] - g[0]) * (x0[0] - g[0]) + (x0[1] - g[1]) * (x0[1] - g[1]) + (x0[2] - g[2]) * (x0[2] - g[2]));
-    const double ntp = sqrt(tp[0] * tp[0] + tp[1] * tp[1] + tp[2] * tp[2]);
-    double nta;
-    if (a.att_dim == 3) nta = sqrt(ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2]);
-    else nta = sqrt(ta[1] * ta[1] + ta[2] * ta[2] + ta[3] * ta[3]) / fmax(fabs(ta[0]), 1e-3);     // tan(theta/2) from the quaternion
-    const double score = 16.6 + 3.12 * r0 + 77.3 * nta - 36.6 * ntp + 2.67 * dist;
-    int b = (int)score;
+    float f[LPT_NF];
+    for (int i = 0; i < 3; i++) { f[i] = (float)x0[i]; f[3 + i] = (float)g[i]; f[6 + i] = (float)tp[i]; }
+    if (a.att_dim == 3) { for (int i = 0; i < 3; i++) f[9 + i] = (float)ta[i]; }
+    else { const double q0 = (fabs(ta[0]) > 1e-3) ? ta[0] : 1e-3; for (int i = 0; i < 3; i++) f[9 + i] = (float)(ta[1 + i] / q0); }   // Rodrigues vector of the quaternion
+    f[12] = (float)(a.round_t ? se3::round1(a.t[src]) : a.t[src]);
+    f[13] = (float)x0[6]; f[14] = (float)x0[9];
+    f[15] = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    f[16] = sqrtf((f[0] - f[3]) * (f[0] - f[3]) + (f[1] - f[4]) * (f[1] - f[4]) + (f[2] - f[5]) * (f[2] - f[5]));
+    f[17] = sqrtf(f[6] * f[6] + f[7] * f[7] + f[8] * f[8]);
+    f[18] = sqrtf(f[9] * f[9] + f[10] * f[10] + f[11] * f[11]);
+#pragma unroll
+    for (int i = 0; i < LPT_NF; i++) f[i] = (f[i] - LPT_MEAN[i]) * LPT_ISTD[i];
+    float score = LPT_W[0];
+    int m = 1;
+#pragma unroll
+    for (int i = 0; i < LPT_NF; i++) score += LPT_W[m++] * f[i];
+#pragma unroll
+    for (int i = 0; i < LPT_NF; i++)
+#pragma unroll
+        for (int j = i; j < LPT_NF; j++) score += LPT_W[m++] * f[i] * f[j];
+    int b = (int)(score * 0.75f);           // 256 buckets over 0 .. 340 predicted factorisations
     b = b < 0 ? 0 : (b > LPT_BUCKETS - 1 ? LPT_BUCKETS - 1 : b);
     return LPT_BUCKETS - 1 - b;        // bucket 0 = predicted longest
 }

@@ -1551,6 +1551,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
      * successive iterations the last rejected trial step was rejected because of the filter, the filter is cleared (at most five
      * times per solve).  Switch: SE3O_FLAG_FILTER_RESET. */
     int rej_filter = 0, n_rej_filter = 0, n_filter_resets = 0;
+    int n_first_ok = 0;          /* iterations whose delta_w = 0 factorisation already had the right inertia (statistics) */
     int in_watchdog = 0, wd_short = 0, wd_trial = 0, nwatch = 0;
     double wd_theta = 0, wd_phi = 0, wd_gphid = 0, wd_fcur = 0, wd_delta = 0;
     ipm_t *wd_save = NULL;
@@ -1596,6 +1597,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
         }
         if (!ok) { status = 3; break; }
         if (delta > 0) delta_last = delta;
+        else n_first_ok++;
         compute_dz(s, mu, s->dx, s->du);
 
         double alpha_max = frac_to_bound_primal(s, s->dx, s->du, tau);
@@ -1900,6 +1902,7 @@ int se3o_solve_from(const se3o_params *p, const se3o_problem *pb, const double *
     sol->status = status; sol->iters = iter; sol->nfact = s->nfact; sol->nls = nls; sol->nsoc = nsoc; sol->nresto = getenv("SE3O_STAT") ? max_consec_short : nresto + nsoft;
     sol->mu = mu;
     if (getenv("SE3O_STAT_WD")) sol->nresto = nwatch;
+    if (getenv("SE3O_STAT_FIRST_OK")) sol->nresto = n_first_ok;
     free(wd_save);
     free(s);
     return status;
