@@ -115,3 +115,46 @@ def test_gpu_restoration_pass_matches_oracle(oracle):
     gm = se3.ops.solve(t(mix["x0"]), t(mix["goal"]), t(mix["tra_pos"]), t(mix["tra_ang"]), t(mix["t"]), ulast=t(ul), round_t=False, params=p)
     assert np.all(gm["status"].cpu().numpy() <= 1)
     assert np.allclose(gm["cost"].cpu().numpy()[64:], cost[:16], rtol=1e-12, atol=0)      # batch-composition invariance holds across the passes
+
+
+def test_filter_reset_and_watchdog_end_the_3000_iteration_shuffle(oracle, emu):
+    """Problem 3475 of the seed-8005 batch (rank 7, third timed step of an 8-GPU bench run): with the restoration phase alone it alternates
+    between restoration and ever shorter regular steps until max_iter = 3000 (1.3 s on one GPU warp).  IPOPT's filter reset heuristic
+    (filter_reset_trigger = 5, max_filter_resets = 5) ends that: both sides converge in ~140 iterations, to the same point."""
+    from tests.common import sample_scenarios
+    sc = sample_scenarios(4096, 8005)
+    i = 3475
+    one = lambda k: np.ascontiguousarray(sc[k][i:i + 1])  # noqa: E731
+    p = oracle.default_params(tol=1e-8)
+    assert p.flags & 32 and p.flags & 16
+    so = oracle.solve_batch(p, one("x0"), one("goal"), one("tra_pos"), one("tra_ang"), one("t"), round_t=True)
+    assert so["status"][0] == 0 and so["iters"][0] < 300
+    p.flags &= ~32
+    p.max_iter = 600                                                       # (enough to see it: 3000 would only take longer)
+    slow = oracle.solve_batch(p, one("x0"), one("goal"), one("tra_pos"), one("tra_ang"), one("t"), round_t=True, want_traj=False)
+    assert slow["status"][0] == 2 and slow["iters"][0] == 600
+    pe = emu.params_from(oracle.default_params(tol=1e-8))
+    se = emu.solve(pe, sc["x0"][i], sc["goal"][i], sc["tra_pos"][i], sc["tra_ang"][i], float(sc["t"][i]), round_t=True)
+    assert se["status"] == 0 and abs(se["iters"] - so["iters"][0]) <= 3
+    assert abs(se["cost"] - so["cost"][0]) <= 1e-6 * abs(so["cost"][0])
+    assert np.abs(se["state_traj_opt"] - so["X"][0].reshape(51, 13)).max() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_iteration_tail_of_the_bench_batches(oracle):
+    """The batch that holds the shuffle problem, through the product: every solve converges, none runs past 300 iterations, and the long
+    ones agree with the oracle."""
+    import torch
+    import learningagileflight_se3_b200 as se3
+    from tests.common import sample_scenarios
+    sc = sample_scenarios(4096, 8005)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")  # noqa: E731
+    g = se3.ops.objective(t(sc["x0"]), t(sc["goal"]), t(sc["gate"]), t(sc["tra_pos"]), t(sc["tra_ang"]), t(sc["t"]))
+    st, it = g["status"].cpu().numpy(), g["iters"].cpu().numpy()
+    assert np.all(st <= 1) and it.max() < 300, (np.bincount(st, minlength=5), it.max())
+    idx = np.argsort(-it)[:6]
+    so = oracle.solve_batch(oracle.default_params(tol=1e-8), sc["x0"][idx], sc["goal"][idx], sc["tra_pos"][idx], sc["tra_ang"][idx], sc["t"][idx],
+                            round_t=True, want_traj=False)
+    cost = g["cost"].cpu().numpy()[idx]
+    rel = np.abs(cost - so["cost"]) / np.abs(so["cost"])
+    assert np.all(so["status"] <= 1) and (rel <= 1e-6).sum() >= 5           # (a 100+-iteration solve may end in a neighbouring stationary point: counted)
