@@ -693,14 +693,15 @@ int device_setup()
 // Resident CTAs per SM for a launch of `nproblems`; the solver kernel is instantiated for 2 (255 registers) and for CTAS_PER_SM
 // (168 registers).  Fewer, fatter warps mean a lower per-problem latency (more registers, a larger share of the instruction
 // cache).  Measured on B200 (profiles/README.md): up to ~2 waves of problems the makespan is set by single-problem latency and
-// 2 CTAs/SM (8 warps) win by ~10%; for large batches 3 CTAs/SM (12 warps) give ~3% more throughput.
-// SE3MPC_CTAS_PER_SM overrides (tuning).
+// 2 CTAs/SM (8 warps) win by ~10%.  For large batches 3 CTAs/SM (12 warps) used to give ~3% more throughput; since the factor
+// sweep lost its divergent branches (round 2) 8 warps win at every size (65 536 problems: 84.7 vs 83.3 k solves/s, 262 144: 85.1
+// vs 83.8), so 2 is the policy and the 12-warp instance is kept for SE3MPC_CTAS_PER_SM=3 (tuning).
 int ctas_per_sm_for(int nproblems)
 {
     static const int forced = [] { const char *e = getenv("SE3MPC_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
     if (forced >= 1 && forced <= CTAS_PER_SM) return forced;
-    const int full = num_sms() * CTAS_PER_SM * WARPS_PER_CTA;
-    return (CTAS_PER_SM > 2 && nproblems <= 4 * full) ? 2 : CTAS_PER_SM;
+    (void)nproblems;
+    return 2;
 }
 
 int slots_for(int nproblems)
