@@ -592,25 +592,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) se3mpc_kkt_step_kernel(
     if (a.dump && a.dump_stage >= 0 && a.dump_stage < N) {
         // the stage matrices as the factor sweep's S1 builds them: constant parts (init_AB), then the packed record through the lane table
         __syncwarp();
-        se3::init_AB(c);
+        // (in the state order of the factor sweep, xpos<SE3_PERM>; the dump is handed out in the natural order)
+        constexpr bool PERM = SE3_PERM != 0;
+        se3::init_AB(c, PERM);
         double *sbase = reinterpret_cast<double *>(&sm);
         const se3::LaneTab t = SE3_LTAB(c)[lane];
         const se3::GP R = se3::rec(c, a.dump_stage);
         const double r0 = R[lane], r1 = R[32 + lane], r2 = R[64 + lane], r3 = R[96 + lane];
-        sbase[t.f0] = r0;
+        sbase[PERM ? t.pf0 : t.f0] = r0;
         const double w1 = r1 + (t.addd[1] ? a.delta_w : 0.0), w2 = r2 + (t.addd[2] ? a.delta_w : 0.0);
         for (int d = 0; d < 4; d++) {
-            if (t.f1[d] >= 0) sbase[t.f1[d]] = w1;
-            if (t.f2[d] >= 0) sbase[t.f2[d]] = w2;
+            const int f1 = PERM ? t.pf1[d] : t.f1[d], f2 = PERM ? t.pf2[d] : t.f2[d];
+            if (f1 >= 0) sbase[f1] = w1;
+            if (f2 >= 0) sbase[f2] = w2;
         }
-        if (t.f3 >= 0) sbase[t.f3] = r3;
+        if ((PERM ? t.pf3 : t.f3) >= 0) sbase[PERM ? t.pf3 : t.f3] = r3;
         __syncwarp();
+        // slot of row / column e of the natural 16- resp. 24-wide images (13..15: the padding slots, in order)
+        auto slot = [](int e) { return (e < 13) ? se3::xpos<PERM>(e) : (e < 16) ? (PERM ? (e == 13 ? 6 : e == 14 ? 7 : 15) : e) : e; };
         double *o = a.dump + (size_t)pb * (16 * se3::SR + 24 * se3::SQ);
         for (int e = lane; e < 16 * se3::SR; e += 32) {           // dense [16][SR] image of the transposed shared-memory operand
             const int i = e / se3::SR, j = e % se3::SR;
-            o[e] = (j < 24) ? sm.Rb[se3::rbi(i, j)] : 0.0;
+            o[e] = (j < 24) ? sm.Rb[se3::rbi(slot(i), slot(j))] : 0.0;
         }
-        for (int e = lane; e < 24 * se3::SQ; e += 32) o[16 * se3::SR + e] = sm.Qa[e];
+        for (int e = lane; e < 24 * se3::SQ; e += 32) {
+            const int i = e / se3::SQ, j = e % se3::SQ;
+            o[16 * se3::SR + e] = (j < 16 || j >= 24) ? sm.Qa[slot(i) * se3::SQ + slot(j)] : sm.Qa[slot(i) * se3::SQ + j];
+        }
     }
 }
 
