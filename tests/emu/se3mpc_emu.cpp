@@ -59,6 +59,11 @@ extern "C" double se3emu_round1(double t) { return round1(t); }
 extern "C" void se3emu_rd2quat(const double *a, double *q) { rd2quat(a, q); }
 extern "C" size_t se3emu_smem_bytes(void) { return sizeof(WarpSmem); }
 extern "C" size_t se3emu_slot_bytes(void) { return SLOT_DOUBLES * sizeof(double); }
+// state order of the DMMA factor sweep and its list of structurally zero products (tests/test_state_order.py)
+extern "C" int se3emu_perm(void) { return SE3_PERM; }
+extern "C" int se3emu_xpos(int i) { return xpos<SE3_PERM != 0>(i); }
+extern "C" int se3emu_xidx(int p) { return xidx<SE3_PERM != 0>(p); }
+extern "C" int se3emu_ab_block(int tile, int ks4) { return ab_block(tile, ks4) ? 1 : 0; }
 
 // one Newton step from a given iterate (reference ordering w=[x0,u0,...,xN]); mirrors se3o_kkt_step
 extern "C" int se3emu_kkt_step(const se3mpc_params *p, const double *goal, const double *tra_pos, const double *tra_q,
