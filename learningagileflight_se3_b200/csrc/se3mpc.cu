@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) se3mpc_kkt_step_kernel(
         const se3::GP R = se3::rec(c, a.dump_stage);
         const double r0 = R[lane], r1 = R[32 + lane], r2 = R[64 + lane], r3 = R[96 + lane];
         sbase[PERM ? t.pf0 : t.f0] = r0;
-        const double w1 = r1 + (t.addd[1] ? a.delta_w : 0.0), w2 = r2 + (t.addd[2] ? a.delta_w : 0.0);
+        const double w1 = r1 + (t.addd[0] ? a.delta_w : 0.0), w2 = r2 + (t.addd[1] ? a.delta_w : 0.0);
         for (int d = 0; d < 4; d++) {
             const int f1 = PERM ? t.pf1[d] : t.f1[d], f2 = PERM ? t.pf2[d] : t.f2[d];
             if (f1 >= 0) sbase[f1] = w1;
@@ -670,6 +670,7 @@ int num_sms()
 
 constexpr size_t HDR_BYTES = 256;
 constexpr size_t SOLVER_SMEM = se3::LTAB_BYTES + sizeof(se3::WarpSmem) * WARPS_PER_CTA;
+static_assert(CTAS_PER_SM * (SOLVER_SMEM + 1024) <= 228 * 1024, "CTAS_PER_SM resident CTAs (1 KB reserved each) must fit the 228 KB of an sm_100 SM");
 constexpr int MAX_DEVICES = 64;
 
 // Function attributes are per device (per primary context): the opt-in to more than 48 KB of dynamic shared memory has to be made on
