@@ -57,3 +57,26 @@ def test_skipped_products_are_structurally_zero(maps, oracle):
                 assert L.se3emu_ab_block(tile, ks4), f"the kernel skips the non-zero block k-step {ks4} x column tile {tile}"
     # and the list is tight: the kernel executes no block that is always zero
     assert sum(L.se3emu_ab_block(t, k) for t in range(3) for k in range(4)) == int(nz.sum())
+
+
+def test_rv_columns_of_A_hold_only_one_and_dt(maps, oracle):
+    """SE3_RV_COLS / SE3_RV_ROWS replace eight DMMAs per stage by register arithmetic; they rely on column r_t of A = I + dt df/dx being the
+    unit vector e_{r_t}, column v_t being dt e_{r_t} + e_{v_t}, and on (r_t, v_t) sitting in neighbouring slots (2 t, 2 t + 1) of tile 0."""
+    L, xpos, xidx = maps
+    if not L.se3emu_perm():
+        pytest.skip("natural state order")
+    O, p, rng = oracle, oracle.default_params(), np.random.default_rng(11)
+    for t in range(3):
+        assert xpos[t] == 2 * t and xpos[3 + t] == 2 * t + 1
+    for _ in range(20):
+        x = rng.normal(size=13) * 3.0
+        x[6:10] /= np.linalg.norm(x[6:10])
+        u = rng.uniform(0.0, 4.0, 4)
+        Jx, _ = O.dyn_jac(p, x, u)
+        A = np.eye(13) + p.dt * Jx
+        for t in range(3):
+            er, ev = np.zeros(13), np.zeros(13)
+            er[t] = 1.0
+            ev[t], ev[3 + t] = p.dt, 1.0
+            assert np.array_equal(A[:, t], er)
+            assert np.array_equal(A[:, 3 + t], ev)
