@@ -36,15 +36,13 @@ def test_skipped_products_are_structurally_zero(maps, oracle):
     if not L.se3emu_perm():
         pytest.skip("natural state order: no product is skipped")
     O, p, rng = oracle, oracle.default_params(), np.random.default_rng(7)
-    dt = p.dt
     kstep = lambda slot: 2 * (slot // 8) + (slot & 1)          # noqa: E731  k-step that covers a slot
     nz = np.zeros((4, 3), dtype=bool)                            # (k-step, column tile) blocks of [A | B] with a non-zero entry somewhere
     for _ in range(50):
         x = rng.normal(size=13) * 2.0
         x[6:10] /= np.linalg.norm(x[6:10])
         u = rng.uniform(0.0, 4.0, 4)
-        Jx, Ju = O.dyn_jac(p, x, u)
-        A, B = np.eye(13) + dt * Jx, dt * Ju
+        A, B = O.dyn_jac(p, x, u)          # Jacobians of the Euler step x + dt f(x, u): A = I + dt df/dx, B = dt df/du
         for j in range(13):                                      # row j of A: the equation of component j (contraction index of the products)
             for i in range(13):
                 if A[j, i] != 0.0:
@@ -72,8 +70,7 @@ def test_rv_columns_of_A_hold_only_one_and_dt(maps, oracle):
         x = rng.normal(size=13) * 3.0
         x[6:10] /= np.linalg.norm(x[6:10])
         u = rng.uniform(0.0, 4.0, 4)
-        Jx, _ = O.dyn_jac(p, x, u)
-        A = np.eye(13) + p.dt * Jx
+        A, _ = O.dyn_jac(p, x, u)
         for t in range(3):
             er, ev = np.zeros(13), np.zeros(13)
             er[t] = 1.0
